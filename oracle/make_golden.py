@@ -1,0 +1,135 @@
+"""Freeze golden vectors from the REFERENCE's own modules (run in the build container only).
+
+    python oracle/make_golden.py          # writes tests/golden/*.npz
+
+The reference ships no tests or fixtures, so parity is pinned on outputs of
+its modules executed here on the torch CPU backend: DepthwiseSeparableBlock
+(models/students/transform_blocks/depthwise_separable_conv.py), KLDivergenceLoss,
+EnsembleKLDivergenceLoss, WeightedHintMSELoss, MSELoss (losses/*.py), plus real CIFAR-10
+ResNet44 teacher logits from checkpoints/cifar10/resnet44.th.  Modules are loaded by file
+path so none of the reference's package-level side effects run.  /root/reference is not
+available on the GPU box; only the .npz files travel.
+"""
+import importlib.util
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+REF = os.environ.get("KDCC_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def _load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def block_case(ref_block_cls, tag, N, Ci, Co, H, W, k, d, p, seed, dtype=torch.float32):
+    torch.manual_seed(seed)
+    blk = ref_block_cls(Ci, Co, k, p, d, Ci, None).to(dtype)
+    # spread the weights a little so that every tap matters
+    with torch.no_grad():
+        blk.separable_conv.weight.mul_(2.0)
+    x = torch.randn(N, Ci, H, W, dtype=dtype, requires_grad=True)
+    y = blk(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    f = lambda t: t.detach().to(torch.float32).numpy()
+    return {
+        f"{tag}/geom": np.array([N, Ci, Co, H, W, k, d, p], np.int64),
+        f"{tag}/x": f(x), f"{tag}/w_dw": f(blk.separable_conv.weight), f"{tag}/w_pw": f(blk.pointwise_conv.weight),
+        f"{tag}/y": f(y), f"{tag}/dy": f(dy), f"{tag}/dx": f(x.grad),
+        f"{tag}/dw_dw": f(blk.separable_conv.weight.grad), f"{tag}/dw_pw": f(blk.pointwise_conv.weight.grad),
+    }
+
+
+def loss_case(tag, module, args, grads_of=0):
+    args = [a.clone().requires_grad_(i == grads_of) for i, a in enumerate(args)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        loss = module(*args)
+    loss.backward()
+    out = {f"{tag}/loss": np.array(loss.item(), np.float64), f"{tag}/grad": args[grads_of].grad.numpy()}
+    for i, a in enumerate(args):
+        out[f"{tag}/arg{i}"] = a.detach().numpy()
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)  # deterministic reduction order
+    blockmod = _load("ref_dsc", "models/students/transform_blocks/depthwise_separable_conv.py")
+    Block = blockmod.DepthwiseSeparableBlock
+    kl = _load("ref_kl", "losses/KLDiv.py").KLDivergenceLoss
+    ekl = _load("ref_ekl", "losses/EnsembleKLDiv.py").EnsembleKLDivergenceLoss
+    whm = _load("ref_whm", "losses/WeightedHintMSELoss.py").WeightedHintMSELoss
+    mse = _load("ref_mse", "losses/MSELoss.py").MSELoss
+
+    # ---- cheap-conv block: forward + backward -------------------------------------------
+    blocks = {}
+    #                 tag            N  Ci  Co   H   W  k  d   p  seed
+    for spec in [("cifar_k3",        4, 64, 64,  8,  8, 3, 1,  1, 11),   # cfg/cifar10/resnet44/config1.json:84-89
+                 ("city_k9d5",       1, 16, 24, 26, 31, 9, 5, 20, 12),   # cfg/cityscapes/51M_deeplab_all.json:117-122
+                 ("ragged_k3d2",     2,  8, 16,  9, 12, 3, 2,  2, 13),
+                 ("k5",              1,  8,  8, 10, 10, 5, 1,  2, 14),
+                 ("shrink_k3p0",     2,  8, 24,  7, 11, 3, 1,  0, 15),   # output smaller than input
+                 ("onepix_k1",       3, 16,  8,  5,  4, 1, 1,  0, 16)]:
+        blocks.update(block_case(Block, *spec))
+    # fp64 run of the Cityscapes geometry: tolerance anchor for the fp32 comparisons
+    blocks.update(block_case(Block, "city_k9d5_f64", 1, 16, 24, 26, 31, 9, 5, 20, 12, dtype=torch.float64))
+    np.savez_compressed(os.path.join(OUT, "block.npz"), **blocks)
+
+    # ---- losses ---------------------------------------------------------------------------
+    losses = {}
+    torch.manual_seed(21)
+    s, t = 3 * torch.randn(2, 19, 12, 13), 3 * torch.randn(2, 19, 12, 13)
+    for T in (1, 2, 5):
+        losses.update(loss_case(f"kl_T{T}", kl(temperature=T), [s, t]))
+    losses[f"kl_T1/T"] = np.array(1.0); losses["kl_T2/T"] = np.array(2.0); losses["kl_T5/T"] = np.array(5.0)
+    # extreme logits: softmax must be max-subtracted
+    big_s, big_t = 40 * torch.randn(3, 19, 5, 7), 40 * torch.randn(3, 19, 5, 7)
+    losses.update(loss_case("kl_big", kl(temperature=1), [big_s, big_t])); losses["kl_big/T"] = np.array(1.0)
+
+    # real CIFAR-10 ResNet44 teacher logits (cfg/cifar10/resnet44/config1.json: KLDivergenceLoss T=5, batch 32)
+    resnet = _load("ref_cifar_resnet", "models/cifar_models/resnet.py")
+    teacher = resnet.resnet44()
+    ck = torch.load(os.path.join(REF, "checkpoints/cifar10/resnet44.th"), map_location="cpu", weights_only=False)
+    teacher.load_state_dict({k.replace("module.", "", 1): v for k, v in ck["state_dict"].items()})
+    teacher.eval()
+    torch.manual_seed(0)
+    with torch.no_grad():
+        t_logits = teacher(torch.randn(32, 3, 32, 32))
+    s_logits = t_logits + 0.5 * torch.randn_like(t_logits)
+    losses.update(loss_case("kl_cifar_T5", kl(temperature=5), [s_logits, t_logits])); losses["kl_cifar_T5/T"] = np.array(5.0)
+
+    # ensemble KL: targets are probabilities (mean of 3 teachers' softmaxes); one variant has exact zeros
+    torch.manual_seed(22)
+    s = 2 * torch.randn(2, 19, 8, 8)
+    probs = torch.stack([torch.softmax(2 * torch.randn(2, 19, 8, 8), 1) for _ in range(3)]).mean(0)
+    losses.update(loss_case("ekl", ekl(), [s, probs]))
+    onehot = torch.zeros(2, 19, 8, 8).scatter_(1, torch.randint(0, 19, (2, 1, 8, 8)), 1.0)
+    losses.update(loss_case("ekl_onehot", ekl(), [s, onehot]))
+
+    # hint losses
+    torch.manual_seed(23)
+    s, t = torch.randn(2, 16, 8, 9), torch.randn(2, 16, 8, 9)
+    w1, w2 = torch.rand(16), torch.rand(2, 16)
+    losses.update(loss_case("whint_vec", whm(), [s, t, w1]))
+    losses.update(loss_case("whint_tab", whm(), [s, t, w2]))
+    losses.update(loss_case("mse_nc1000", mse(num_classes=1000), [s, t])); losses["mse_nc1000/nc"] = np.array(1000.0)
+    losses.update(loss_case("mse_nc1", mse(num_classes=1), [s, t])); losses["mse_nc1/nc"] = np.array(1.0)
+    s4, t4 = torch.randn(3, 24, 1, 1), torch.randn(3, 24, 1, 1)          # degenerate 1x1 maps
+    losses.update(loss_case("mse_1x1", mse(num_classes=19), [s4, t4])); losses["mse_1x1/nc"] = np.array(19.0)
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **losses)
+
+    for fn in ("block.npz", "losses.npz"):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

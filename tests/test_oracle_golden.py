@@ -1,0 +1,121 @@
+"""Pins the CPU oracle (C restatement + torch port) against fixtures frozen from the
+reference's own modules by oracle/make_golden.py.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from oracle import torch_port as tp
+
+BLOCK_CASES = ["cifar_k3", "city_k9d5", "ragged_k3d2", "k5", "shrink_k3p0", "onepix_k1"]
+RTOL = 1e-5  # north_star: 1e-5 relative in fp32
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("tag", BLOCK_CASES)
+def test_c_oracle_block_matches_reference(golden_block, tag):
+    g = golden_block
+    N, Ci, Co, H, W, k, d, p = [int(v) for v in g[f"{tag}/geom"]]
+    y, dx, dw_dw, dw_pw = orc.block_fwd_bwd(g[f"{tag}/x"], g[f"{tag}/w_dw"], g[f"{tag}/w_pw"], k, d, p,
+                                            dy=g[f"{tag}/dy"])
+    assert y.shape == g[f"{tag}/y"].shape
+    assert relerr(y, g[f"{tag}/y"]) < RTOL
+    assert relerr(dx, g[f"{tag}/dx"]) < RTOL
+    assert relerr(dw_dw, g[f"{tag}/dw_dw"]) < RTOL
+    assert relerr(dw_pw, g[f"{tag}/dw_pw"]) < RTOL
+
+
+def test_c_oracle_closer_to_fp64_reference_than_fp32_reference(golden_block):
+    """The double-accumulating oracle must sit at least as close to the reference run in
+    fp64 as the reference's own fp32 run does (tolerance anchor)."""
+    g, tag = golden_block, "city_k9d5"
+    N, Ci, Co, H, W, k, d, p = [int(v) for v in g[f"{tag}/geom"]]
+    y, dx, dw_dw, dw_pw = orc.block_fwd_bwd(g[f"{tag}/x"], g[f"{tag}/w_dw"], g[f"{tag}/w_pw"], k, d, p,
+                                            dy=g[f"{tag}/dy"])
+    for name, mine in (("y", y), ("dx", dx), ("dw_dw", dw_dw), ("dw_pw", dw_pw)):
+        f64 = g[f"{tag}_f64/{name}"]
+        assert relerr(mine, f64) <= relerr(g[f"{tag}/{name}"], f64) + 2e-7
+
+
+@pytest.mark.parametrize("tag", BLOCK_CASES)
+def test_torch_port_block_matches_reference(golden_block, tag):
+    g = golden_block
+    N, Ci, Co, H, W, k, d, p = [int(v) for v in g[f"{tag}/geom"]]
+    x = torch.from_numpy(g[f"{tag}/x"]).requires_grad_(True)
+    w_dw = torch.from_numpy(g[f"{tag}/w_dw"]).requires_grad_(True)
+    w_pw = torch.from_numpy(g[f"{tag}/w_pw"]).requires_grad_(True)
+    y = tp.block_forward(x, w_dw, w_pw, p, d)
+    y.backward(torch.from_numpy(g[f"{tag}/dy"]))
+    assert relerr(y.detach().numpy(), g[f"{tag}/y"]) < RTOL
+    assert relerr(x.grad.numpy(), g[f"{tag}/dx"]) < RTOL
+    assert relerr(w_dw.grad.numpy(), g[f"{tag}/dw_dw"]) < RTOL
+    assert relerr(w_pw.grad.numpy(), g[f"{tag}/dw_pw"]) < RTOL
+
+
+@pytest.mark.parametrize("tag", ["kl_T1", "kl_T2", "kl_T5", "kl_big", "kl_cifar_T5"])
+def test_kd_loss_matches_reference(golden_losses, tag):
+    g = golden_losses
+    T = float(g[f"{tag}/T"])
+    loss, ds = orc.kd_loss(g[f"{tag}/arg0"], g[f"{tag}/arg1"], T=T)
+    assert abs(loss - float(g[f"{tag}/loss"])) <= RTOL * abs(float(g[f"{tag}/loss"]))
+    assert relerr(ds, g[f"{tag}/grad"]) < RTOL
+    s = torch.from_numpy(g[f"{tag}/arg0"]).requires_grad_(True)
+    lt = tp.kl_div_loss(s, torch.from_numpy(g[f"{tag}/arg1"]), T)
+    lt.backward()
+    assert abs(float(lt) - float(g[f"{tag}/loss"])) <= RTOL * abs(float(g[f"{tag}/loss"]))
+    assert relerr(s.grad.numpy(), g[f"{tag}/grad"]) < RTOL
+
+
+@pytest.mark.parametrize("tag", ["ekl", "ekl_onehot"])
+def test_ensemble_kd_loss_matches_reference(golden_losses, tag):
+    g = golden_losses
+    loss, ds = orc.kd_loss(g[f"{tag}/arg0"], g[f"{tag}/arg1"], T=1.0, target_is_prob=True)
+    assert abs(loss - float(g[f"{tag}/loss"])) <= RTOL * abs(float(g[f"{tag}/loss"]))
+    assert relerr(ds, g[f"{tag}/grad"]) < RTOL
+    s = torch.from_numpy(g[f"{tag}/arg0"]).requires_grad_(True)
+    lt = tp.ensemble_kl_loss(s, torch.from_numpy(g[f"{tag}/arg1"]))
+    lt.backward()
+    assert abs(float(lt) - float(g[f"{tag}/loss"])) <= RTOL * abs(float(g[f"{tag}/loss"]))
+
+
+@pytest.mark.parametrize("tag", ["whint_vec", "whint_tab"])
+def test_weighted_hint_matches_reference(golden_losses, tag):
+    g = golden_losses
+    loss, ds = orc.hint_loss(g[f"{tag}/arg0"], g[f"{tag}/arg1"], w=g[f"{tag}/arg2"], scale=1.0)
+    assert abs(loss - float(g[f"{tag}/loss"])) <= RTOL * abs(float(g[f"{tag}/loss"]))
+    assert relerr(ds, g[f"{tag}/grad"]) < RTOL
+    s = torch.from_numpy(g[f"{tag}/arg0"]).requires_grad_(True)
+    lt = tp.weighted_hint_mse(s, torch.from_numpy(g[f"{tag}/arg1"]), torch.from_numpy(g[f"{tag}/arg2"]))
+    lt.backward()
+    assert relerr(s.grad.numpy(), g[f"{tag}/grad"]) < RTOL
+
+
+@pytest.mark.parametrize("tag", ["mse_nc1000", "mse_nc1", "mse_1x1"])
+def test_mse_matches_reference(golden_losses, tag):
+    g = golden_losses
+    nc = float(g[f"{tag}/nc"])
+    loss, ds = orc.hint_loss(g[f"{tag}/arg0"], g[f"{tag}/arg1"], w=None, scale=nc)
+    assert abs(loss - float(g[f"{tag}/loss"])) <= RTOL * abs(float(g[f"{tag}/loss"]))
+    assert relerr(ds, g[f"{tag}/grad"]) < RTOL
+    s = torch.from_numpy(g[f"{tag}/arg0"]).requires_grad_(True)
+    lt = tp.mse_loss(s, torch.from_numpy(g[f"{tag}/arg1"]), nc)
+    lt.backward()
+    assert relerr(s.grad.numpy(), g[f"{tag}/grad"]) < RTOL
+
+
+def test_empty_batch_and_layout_roundtrip():
+    x = np.zeros((0, 8, 4, 4), np.float32)
+    w = np.ones((8, 1, 3, 3), np.float32)
+    assert orc.dw_fwd(x, w, 3, 1, 1).shape == (0, 8, 4, 4)
+    a = np.random.RandomState(0).randn(2, 5, 3, 4).astype(np.float32)
+    nhwc = np.empty((2, 3, 4, 5), np.float32)
+    back = np.empty_like(a)
+    L = orc.lib()
+    L.orc_nchw_to_nhwc(orc._ptr(a), orc._ptr(nhwc), 2, 5, 12)
+    L.orc_nhwc_to_nchw(orc._ptr(nhwc), orc._ptr(back), 2, 5, 12)
+    assert np.array_equal(a, back)
+    assert np.array_equal(nhwc, a.transpose(0, 2, 3, 1))
