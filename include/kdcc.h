@@ -1,0 +1,124 @@
+/*
+ * kdcc.h -- C ABI of libkdcc.so: the sm_100a (B200) kernels behind the distillation hot path of
+ * lehduong/Knowledge-Distillation-by-Replacing-Cheap-Conv.
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); each entry point below
+ * replaces the torch library call(s) that one reference call site makes, cited as
+ * reference-file:line.  INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator); the library
+ *     allocates nothing persistent apart from cached TMA descriptors / function attributes;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - entry points are re-entrant and hold no thread-affine state (autograd calls backward from its
+ *     own worker thread);
+ *   - activations are NHWC-physical (torch.channels_last): x[n][h][w][c]; logits carry explicit strides;
+ *   - dtype: KDCC_F32 (parity path, 1e-5 relative) or KDCC_BF16 (production path, fp32 accumulate);
+ *   - return 0 on success, a negative KDCC_E* code for bad arguments / unsupported shapes (there is
+ *     NO CPU or library fallback), or a positive cudaError_t.  kdcc_strerror() names any of them.
+ */
+#ifndef KDCC_H_
+#define KDCC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDCC_VERSION 100 /* round 1 */
+
+enum { KDCC_F32 = 0, KDCC_BF16 = 1 };
+enum { KDCC_LAYOUT_NHWC = 0, KDCC_LAYOUT_NCHW = 1 };
+
+enum {
+  KDCC_OK = 0,
+  KDCC_EINVAL = -1,      /* null pointer / non-positive dimension / bad enum */
+  KDCC_ESHAPE = -2,      /* shape not supported by the sm_100a kernels (e.g. C % 8 != 0 in bf16) */
+  KDCC_EWORKSPACE = -3,  /* workspace smaller than kdcc_*_workspace_bytes() says */
+  KDCC_EALIGN = -4,      /* pointer not 16-byte aligned */
+  KDCC_EDEVICE = -5,     /* not an sm_100 device / driver entry point missing */
+};
+
+typedef void *kdcc_stream_t; /* cudaStream_t */
+
+int kdcc_version(void);
+const char *kdcc_strerror(int code);
+
+/* Which implementation a call would dispatch to (for tests / profiles): returns a static string such
+ * as "dw_fwd_tma_k9" or "dw_fwd_direct".  op: 0 = dw_fwd, 1 = dw_bwd, 2 = pw_fwd, 3 = pw_bwd_dx,
+ * 4 = pw_bwd_dw. */
+const char *kdcc_dispatch_name(int op, int N, int H, int W, int C, int Cout, int k, int dil, int pad,
+                               int dtype);
+
+/* ---- depthwise k x k, stride 1, zero padding, dilation `dil` -----------------------------------
+ * Replaces self.separable_conv(x)  (models/students/transform_blocks/depthwise_separable_conv.py:7-8,12
+ * -> F.conv2d groups=C).  x [N,H,W,C], w fp32 [C,k,k] (the (C,1,k,k) parameter, contiguous),
+ * bias fp32 [C] or NULL, y [N,Ho,Wo,C] with Ho = H + 2*pad - dil*(k-1). */
+int kdcc_dw_fwd(const void *x, const float *w, const float *bias, void *y, int N, int H, int W, int C,
+                int k, int dil, int pad, int dtype, kdcc_stream_t stream);
+
+/* Autograd backward of the call above (depthwise_separable_conv.py:12 under loss.backward(),
+ * trainer/layerwise_trainer.py:235).  dx [N,H,W,C] (NULL: input needs no grad), dw fp32 [C,k,k]
+ * (NULL: frozen), dbias fp32 [C] or NULL.  Deterministic two-stage reduction, no atomics. */
+size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, int dil, int pad, int dtype);
+int kdcc_dw_bwd(const void *x, const float *w, const void *dy, void *dx, float *dw, float *dbias,
+                void *workspace, size_t workspace_bytes, int N, int H, int W, int C, int k, int dil,
+                int pad, int dtype, kdcc_stream_t stream);
+
+/* ---- pointwise 1x1 = GEMM ----------------------------------------------------------------------
+ * Replaces self.pointwise_conv(x)  (depthwise_separable_conv.py:9,13).  x [M,K] (M = N*H*W pixels,
+ * K = C_in), w [Nc,K] in the activation dtype (the (Co,C,1,1) parameter, cast by kdcc_cast_f32),
+ * out[m][n] = sum_k x[m][k] w[n][k].  Optional fused epilogue on the second output:
+ *   y_act = relu?( out * scale[n] + shift[n] )   (eval-mode BN fold + ReLU, SURVEY.md F9;
+ *   scale NULL -> 1, shift NULL -> 0; shift alone is the conv bias).
+ * y_raw (the tensor the hint hook captures) and y_act may each be NULL, not both. */
+int kdcc_pw_fwd(const void *x, const void *w, const float *scale, const float *shift, int relu,
+                void *y_raw, void *y_act, long M, int K, int Nc, int dtype, kdcc_stream_t stream);
+
+/* Autograd backward of the call above.  dx[m][k] = sum_n dy[m][n] w[n][k];
+ * dw[n][k] = sum_m dy[m][n] x[m][k] (fp32 out, deterministic split-M reduction). */
+size_t kdcc_pw_bwd_workspace_bytes(int which /*0 = dx, 1 = dw*/, long M, int K, int Nc, int dtype);
+int kdcc_pw_bwd_dx(const void *dy, const void *w, void *dx, void *workspace, size_t workspace_bytes,
+                   long M, int K, int Nc, int dtype, kdcc_stream_t stream);
+int kdcc_pw_bwd_dw(const void *dy, const void *x, float *dw, void *workspace, size_t workspace_bytes,
+                   long M, int K, int Nc, int dtype, kdcc_stream_t stream);
+
+/* ---- losses ------------------------------------------------------------------------------------
+ * kdcc_kd_loss replaces losses/KLDiv.py:19-23 (target_is_prob = 0) and losses/EnsembleKLDiv.py:18-22
+ * (target_is_prob = 1, T = 1): one pass reads s and t, does both softmaxes in registers, writes
+ *   *loss_out = T^2/(N*HW) * sum_pix KL(p_t || p_s)          (fp32 device scalar)
+ *   ds        = grad_scale * T/(N*HW) * (softmax(s/T) - p_t)  (same dtype/strides as s; NULL: skip)
+ * Element (n,c,q) lives at base + n*batch_stride + c*class_stride + q*pixel_stride (elements), so
+ * NCHW logits are (C*HW, HW, 1) and channels-last logits are (HW*C, 1, C). */
+size_t kdcc_loss_workspace_bytes(void);
+int kdcc_kd_loss(const void *s, const void *t, void *ds, float *loss_out, void *workspace,
+                 size_t workspace_bytes, int N, int C, long HW, long batch_stride, long class_stride,
+                 long pixel_stride, float T, int target_is_prob, int dtype, float grad_scale,
+                 kdcc_stream_t stream);
+
+/* kdcc_hint_loss replaces losses/WeightedHintMSELoss.py:12-16 (w given, scale = 1) and
+ * losses/MSELoss.py:14-16 (w NULL, scale = num_classes):
+ *   *loss_out = scale/N * sum_n [ sum_c w[n,c] mean_hw (s-t)^2 / sum_c w[n,c] ]
+ *   ds        = grad_scale * scale * 2 (s-t) w[n,c] / (sum_c w[n,c] * HW * N)
+ * w is fp32 [C] (w_per_sample = 0) or [N,C] (w_per_sample = 1).  layout says how (n,c,q) maps to
+ * memory.  Needs workspace of kdcc_loss_workspace_bytes() + N*C*4 bytes when w is given. */
+int kdcc_hint_loss(const void *s, const void *t, const float *w, int w_per_sample, void *ds,
+                   float *loss_out, void *workspace, size_t workspace_bytes, int N, int C, long HW,
+                   int layout, float scale, int dtype, float grad_scale, kdcc_stream_t stream);
+
+/* ---- small utilities used by the host mirror so no torch arithmetic sits on the path ------------ */
+/* dst_bf16[i] = bf16(src_f32[i]) */
+int kdcc_cast_f32_to_bf16(const float *src, void *dst, long n, kdcc_stream_t stream);
+/* buf[i] *= *dev_scalar   (applies autograd's upstream 0-dim grad to an emitted gradient) */
+int kdcc_scale_inplace(void *buf, const float *dev_scalar, long n, int dtype, kdcc_stream_t stream);
+/* out[j] = sum_m a[m][j]  (bias gradients), a [M,Nc] in dtype, out fp32 */
+int kdcc_colsum(const void *a, float *out, void *workspace, size_t workspace_bytes, long M, int Nc,
+                int dtype, kdcc_stream_t stream);
+size_t kdcc_colsum_workspace_bytes(long M, int Nc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDCC_H_ */

@@ -1,0 +1,14 @@
+"""kdcc -- B200-native (sm_100a) distillation hot path of "Knowledge Distillation by Replacing Cheap Conv".
+
+Host-side mirror of the reference's module interfaces over the C-ABI library libkdcc.so
+(include/kdcc.h).  The directory name carries the upstream repository name; import it as `kdcc`
+(the top-level `kdcc/` shim registers this package under that name).
+"""
+from . import _abi
+from ._abi import KdccError, LIB_PATH
+from .blocks import DepthwiseSeparableBlock
+from .losses import EnsembleKLDivergenceLoss, KLDivergenceLoss, MSELoss, WeightedHintMSELoss
+from . import functional
+
+__all__ = ["DepthwiseSeparableBlock", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
+           "functional", "KdccError", "LIB_PATH"]

@@ -1,0 +1,29 @@
+// Internal interface between the depthwise C-ABI entry points (dw_api.cu) and the kernel files.
+#pragma once
+#include "kdcc_common.cuh"
+
+namespace kdcc {
+
+// ---- direct (gather) kernels: dw_direct.cu --------------------------------------------------------
+template <typename T>
+int dw_direct_fwd(const void *x, const float *w, const float *bias, void *y, int N, int H, int W, int C, int Ho,
+                  int Wo, int k, int dil, int pad, int flip, cudaStream_t st);
+template <typename T>
+int dw_direct_wgrad(const void *x, const void *dy, float *dw, float *dbias, float *part, int N, int H, int W,
+                    int C, int Ho, int Wo, int k, int dil, int pad, cudaStream_t st);
+int dw_direct_wgrad_splits(int N, int Ho, int C, int k, int vn);
+__global__ void dw_wgrad_reduce_kernel(const float *__restrict__ part, float *__restrict__ dw,
+                                       float *__restrict__ dbias, int splits, int C, int KK, int rows);
+
+// ---- TMA-staged bf16 kernels: dw_tma.cu -------------------------------------------------------------
+// A conv (or its transposed form when flip != 0) from `in` [N,Hi,Wi,C] to `out` [N,Ho,Wo,C] with
+// effective padding `pad`:  out[i][j] = sum_{u,v} w'[u][v] in[i + u*dil - pad][j + v*dil - pad].
+bool dw_tma_supported(int C, int k, int dil);
+const char *dw_tma_name(int k, int dil, int which /*0 fwd, 1 wgrad*/);
+int dw_tma_conv(const void *in, const float *w, const float *bias, void *out, int N, int Hi, int Wi, int C, int Ho,
+                int Wo, int k, int dil, int pad, int flip, cudaStream_t st);
+int dw_tma_wgrad_splits(int N, int Ho, int Wo, int C, int k, int dil);
+int dw_tma_wgrad(const void *x, const void *dy, float *dw, float *part, int N, int H, int W, int C, int Ho, int Wo,
+                 int k, int dil, int pad, cudaStream_t st);
+
+}  // namespace kdcc

@@ -1,0 +1,342 @@
+// Pointwise (1x1) convolution as a dense bf16 GEMM on the sm_100a tensor cores:
+// TMA (128B-swizzled tiles) -> shared memory -> tcgen05.mma with the fp32 accumulator in TMEM ->
+// tcgen05.ld epilogue (BN scale/shift + ReLU, dual output) -> global.
+//
+// Reference semantics: models/students/transform_blocks/depthwise_separable_conv.py:9,13 (nn.Conv2d 1x1)
+// and its autograd backward (dX = dY.W, dW = dY^T.X).
+//
+// One kernel template covers the three GEMMs of the block:
+//     D[i][j] = sum_r A(i,r) * B(j,r)
+//   forward   i = pixel m, j = out channel, r = in channel : A = X  (r-contiguous, "K-major"),
+//                                                            B = W  [Co][Ci]      (K-major)
+//   dX        i = pixel m, j = in channel,  r = out channel: A = dY (K-major),
+//                                                            B = W  [Co][Ci] read as (j contiguous, "MN-major")
+//   dW        i = out channel, j = in channel, r = pixel m : A = dY (MN-major), B = X (MN-major); the pixel
+//             reduction is split over CTAs into fp32 partials (deterministic second-stage sum).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2..5 = epilogue (one TMEM lane quadrant each).  Persistent CTAs walk work items round-robin;
+// the accumulator is double-buffered in TMEM so the epilogue of item n overlaps the MMAs of item n+1.
+#include "kdcc_common.cuh"
+#include "pw_kernels.cuh"
+#include "sm100_ptx.cuh"
+
+namespace kdcc {
+
+constexpr int GEMM_BI = 128;   // UMMA M
+constexpr int GEMM_BR = 64;    // reduction elements per stage = one 128-byte swizzle atom of bf16
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  int I, J, R;          // logical extents
+  int tiles_i, tiles_j; // output tiling
+  int splits;           // CTAs sharing one output tile along r (dW only)
+  int rblocks;          // ceil(R / 64)
+  // epilogue
+  __nv_bfloat16 *out_raw, *out_act;  // [I][J] bf16, either may be null
+  const float *scale, *shift;        // per j, may be null
+  int relu;
+  float *out_f32;                    // [splits][I][J] fp32 partials (dW) -- exclusive with the bf16 outputs
+};
+
+template <int BJ>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BI * GEMM_BR * 2;  // 16 KB
+  static constexpr int B_BYTES = BJ * GEMM_BR * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BJ == 256 ? 4 : (BJ == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BJ;  // double-buffered accumulator (power of two >= 32)
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SMEM = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
+};
+
+// UMMA shared-memory descriptors (SWIZZLE_128B, bf16), cf. the canonical layouts of the PTX ISA:
+//  K-major : rows of 128 bytes (64 reduction elements); 8-row groups 1024 bytes apart (SBO).
+//  MN-major: rows of 128 bytes (64 i/j elements) indexed by r; 8-r groups 1024 bytes apart (SBO),
+//            64-element i/j groups `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+template <int BJ, bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t umma_idesc() {
+  // c_format F32 (bits 4-5 = 1), a/b format BF16 (bits 7-9 / 10-12 = 1), majors (bits 15, 16),
+  // N >> 3 (bits 17-22), M >> 4 (bits 24-28)
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         ((uint32_t)(BJ >> 3) << 17) | ((uint32_t)(GEMM_BI >> 4) << 24);
+}
+
+template <int BJ, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                     const GemmParams p) {
+  using Cfg = GemmCfg<BJ>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_gen + Cfg::BAR_OFF + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tm_a);
+    ptx::prefetch_tensormap(&tm_b);
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)));
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long items = (long)p.tiles_i * p.tiles_j * p.splits;
+  const int rb_per_split = (p.rblocks + p.splits - 1) / p.splits;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int s = 0; uint32_t ph = 0;
+    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+      const int split = (int)(item % p.splits);
+      const long tile = item / p.splits;
+      const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+      const int rb0 = split * rb_per_split, rb1 = min(p.rblocks, rb0 + rb_per_split);
+      for (int rb = rb0; rb < rb1; ++rb) {
+        ptx::mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
+        const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+        ptx::mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+        if (!A_MN) {
+          ptx::tma_load_2d(a_dst, &tm_a, full_bar(s), rb * GEMM_BR, ti * GEMM_BI);
+        } else {
+#pragma unroll
+          for (int b = 0; b < GEMM_BI / 64; ++b)
+            ptx::tma_load_2d(a_dst + b * 8192, &tm_a, full_bar(s), ti * GEMM_BI + b * 64, rb * GEMM_BR);
+        }
+        if (!B_MN) {
+          ptx::tma_load_2d(b_dst, &tm_b, full_bar(s), rb * GEMM_BR, tj * BJ);
+        } else {
+#pragma unroll
+          for (int b = 0; b < BJ / 64; ++b)
+            ptx::tma_load_2d(b_dst + b * 8192, &tm_b, full_bar(s), tj * BJ + b * 64, rb * GEMM_BR);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = umma_idesc<BJ, A_MN, B_MN>();
+    int s = 0; uint32_t ph = 0;
+    int as = 0; uint32_t aph = 0;
+    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+      const int split = (int)(item % p.splits);
+      const int rb0 = split * rb_per_split, rb1 = min(p.rblocks, rb0 + rb_per_split);
+      ptx::mbar_wait(tempty_bar(as), aph ^ 1);
+      ptx::tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BJ);
+      for (int rb = rb0; rb < rb1; ++rb) {
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tcgen05_fence_after();
+        const uint32_t a_addr = smem_base + s * Cfg::STAGE_BYTES;
+        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < GEMM_BR / 16; ++k) {
+          // K-major: step 16 elements (32 bytes) inside the swizzle atom; MN-major: step 16 r-rows (2 KB)
+          const uint64_t da = A_MN ? umma_desc(a_addr + k * 2048, 8192, 1024) : umma_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? umma_desc(b_addr + k * 2048, 8192, 1024) : umma_desc(b_addr + k * 32, 16, 1024);
+          ptx::umma_f16(d_tmem, da, db, idesc, (rb > rb0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      ptx::umma_commit(tfull_bar(as));   // accumulator complete -> epilogue
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
+    int as = 0; uint32_t aph = 0;
+    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+      const int split = (int)(item % p.splits);
+      const long tile = item / p.splits;
+      const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+      ptx::mbar_wait(tfull_bar(as), aph);
+      ptx::tcgen05_fence_after();
+      const int row = ti * GEMM_BI + quad * 32 + lane;
+      const uint32_t t_row = tmem_base + (uint32_t)(as * BJ) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < BJ / 32; ++ch) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, v);
+        ptx::tmem_ld_wait();
+        const int col0 = tj * BJ + ch * 32;
+        if (row < p.I && col0 < p.J) {
+          if (p.out_f32 != nullptr) {
+            float *dst = p.out_f32 + ((long)split * p.I + row) * p.J + col0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (col0 + q * 4 < p.J)
+                *reinterpret_cast<uint4 *>(dst + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+            if (p.out_raw != nullptr) {
+              __nv_bfloat16 *dst = p.out_raw + (long)row * p.J + col0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col0 + q * 8 < p.J) {
+                  uint4 o;
+                  o.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+                  o.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+                  o.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+                  o.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+                  *reinterpret_cast<uint4 *>(dst + q * 8) = o;
+                }
+            }
+            if (p.out_act != nullptr) {
+              __nv_bfloat16 *dst = p.out_act + (long)row * p.J + col0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col0 + q * 8 < p.J) {
+                  float f[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int col = col0 + q * 8 + e;
+                    float x = __uint_as_float(v[8 * q + e]);
+                    if (p.scale) x *= __ldg(p.scale + col);
+                    if (p.shift) x += __ldg(p.shift + col);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    f[e] = x;
+                  }
+                  uint4 o;
+                  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                  *reinterpret_cast<uint4 *>(dst + q * 8) = o;
+                }
+            }
+          }
+        }
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// out[i] = sum_s part[s][i]   (fixed order)
+__global__ void reduce_splits_kernel(const float *__restrict__ part, float *__restrict__ out, int splits, long count) {
+  const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= count) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4 *>(part + (long)s * count + i4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4 *>(out + i4) = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// 2-D bf16 map, 128B swizzle: inner extent `inner` (contiguous), outer extent `outer`, box (64, box_outer)
+static int gemm_map(CUtensorMap *m, const void *base, long inner, long outer, int box_outer) {
+  const uint64_t dims[2] = {(uint64_t)inner, (uint64_t)outer};
+  const uint64_t strides[1] = {(uint64_t)inner * 2};
+  const uint32_t box[2] = {64, (uint32_t)box_outer};
+  return make_tmap_bf16(m, base, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int BJ, bool A_MN, bool B_MN>
+static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaStream_t st) {
+  using Cfg = GemmCfg<BJ>;
+  GemmParams p = p0;
+  p.tiles_i = ceil_div(p.I, GEMM_BI);
+  p.tiles_j = ceil_div(p.J, BJ);
+  p.rblocks = ceil_div(p.R, GEMM_BR);
+  CUtensorMap tm_a, tm_b;
+  int rc = A_MN ? gemm_map(&tm_a, a, p.I, p.R, 64) : gemm_map(&tm_a, a, p.R, p.I, GEMM_BI);
+  if (rc) return rc;
+  rc = B_MN ? gemm_map(&tm_b, b, p.J, p.R, 64) : gemm_map(&tm_b, b, p.R, p.J, BJ);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pw_gemm_sm100_kernel<BJ, A_MN, B_MN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long items = (long)p.tiles_i * p.tiles_j * p.splits;
+  const int grid = (int)min(items, (long)kNumSMs);
+  pw_gemm_sm100_kernel<BJ, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(tm_a, tm_b, p);
+  return launch_status();
+}
+
+template <bool A_MN, bool B_MN>
+static int gemm_dispatch_bj(const void *a, const void *b, const GemmParams &p, cudaStream_t st) {
+  if (p.J >= 256 && p.J % 256 == 0) return gemm_launch<256, A_MN, B_MN>(a, b, p, st);
+  if (p.J > 64) return gemm_launch<128, A_MN, B_MN>(a, b, p, st);
+  return gemm_launch<64, A_MN, B_MN>(a, b, p, st);
+}
+
+bool pw_sm100_supported(long M, int K, int Nc) {
+  // 16-byte global strides for TMA and 16-byte epilogue stores
+  return M > 0 && K % 8 == 0 && Nc % 8 == 0 && M < (1L << 31);
+}
+
+int pw_sm100_fwd(const void *x, const void *w, const float *scale, const float *shift, int relu, void *y_raw,
+                 void *y_act, long M, int K, int Nc, cudaStream_t st) {
+  GemmParams p{};
+  p.I = (int)M; p.J = Nc; p.R = K; p.splits = 1;
+  p.out_raw = static_cast<__nv_bfloat16 *>(y_raw);
+  p.out_act = static_cast<__nv_bfloat16 *>(y_act);
+  p.scale = scale; p.shift = shift; p.relu = relu;
+  return gemm_dispatch_bj<false, false>(x, w, p, st);
+}
+
+int pw_sm100_bwd_dx(const void *dy, const void *w, void *dx, long M, int K, int Nc, cudaStream_t st) {
+  // dx[m][k] = sum_n dy[m][n] w[n][k] : j = k, r = n; W [Nc][K] is j-contiguous -> MN-major B
+  GemmParams p{};
+  p.I = (int)M; p.J = K; p.R = Nc; p.splits = 1;
+  p.out_raw = static_cast<__nv_bfloat16 *>(dx);
+  return gemm_dispatch_bj<false, true>(dy, w, p, st);
+}
+
+int pw_sm100_dw_splits(long M, int K, int Nc) {
+  const int bj = (K >= 256 && K % 256 == 0) ? 256 : (K > 64 ? 128 : 64);
+  const long tiles = (long)ceil_div(Nc, GEMM_BI) * ceil_div(K, bj);
+  const long rblocks = ceil_div<long>(M, GEMM_BR);
+  long s = min(max(1L, (long)kNumSMs / tiles), rblocks);
+  const long per = ceil_div<long>(rblocks, s);
+  return (int)ceil_div<long>(rblocks, per);  // every split owns at least one reduction block
+}
+
+int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long M, int K, int Nc, cudaStream_t st) {
+  // dw[n][k] = sum_m dy[m][n] x[m][k] : i = n, j = k, r = m; both operands are MN-major views
+  GemmParams p{};
+  p.I = Nc; p.J = K; p.R = (int)M;
+  p.splits = pw_sm100_dw_splits(M, K, Nc);
+  p.out_f32 = p.splits == 1 ? dw : part;
+  int rc = gemm_dispatch_bj<true, true>(dy, x, p, st);
+  if (rc || p.splits == 1) return rc;
+  const long count = (long)Nc * K;  // multiple of 4 because K % 8 == 0
+  reduce_splits_kernel<<<(unsigned)ceil_div<long>(count / 4, 256), 256, 0, st>>>(part, dw, p.splits, count);
+  return launch_status();
+}
+
+}  // namespace kdcc

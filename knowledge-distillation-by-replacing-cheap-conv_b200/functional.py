@@ -1,0 +1,276 @@
+"""torch.autograd glue over the C ABI: tensors in, raw device pointers + current stream out.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); every arithmetic step of the hot
+path runs in libkdcc.so.  Activations are kept NHWC-physical (torch.channels_last) so no transposes
+are inserted around the kernels.
+
+Reference call sites replaced (reference file:line):
+  depthwise_conv      models/students/transform_blocks/depthwise_separable_conv.py:12
+  pointwise_conv      models/students/transform_blocks/depthwise_separable_conv.py:13
+  kd_loss             losses/KLDiv.py:19-23, losses/EnsembleKLDiv.py:18-22
+  hint_loss           losses/WeightedHintMSELoss.py:12-16, losses/MSELoss.py:14-16
+"""
+import torch
+
+from . import _abi
+
+_DTYPES = {torch.float32: _abi.F32, torch.bfloat16: _abi.BF16}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _abi.KdccError("kdcc kernels need CUDA tensors (sm_100a); got a %s tensor -- there is no CPU fallback"
+                                 % t.device.type)
+
+
+def _dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise _abi.KdccError("kdcc supports float32 and bfloat16 activations, got %s" % t.dtype)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _nhwc(t):
+    """NCHW-logical tensor in NHWC-physical memory (no copy when it already is)."""
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _empty_nhwc(n, c, h, w, like):
+    return torch.empty((n, c, h, w), dtype=like.dtype, device=like.device, memory_format=torch.channels_last)
+
+
+def cast_weight(w_f32, dtype):
+    """fp32 master parameter -> activation dtype through kdcc_cast_f32_to_bf16 (no torch arithmetic)."""
+    if dtype == torch.float32:
+        return w_f32.contiguous()
+    out = torch.empty(w_f32.shape, dtype=torch.bfloat16, device=w_f32.device)
+    src = w_f32.contiguous()
+    _abi.check(_abi.lib().kdcc_cast_f32_to_bf16(_ptr(src), _ptr(out), src.numel(), _stream()), "kdcc_cast_f32_to_bf16")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# depthwise
+# ---------------------------------------------------------------------------------------------------
+class _DepthwiseConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, k, dil, pad):
+        _require_cuda(x, weight, bias)
+        x = _nhwc(x)
+        N, C, H, W = x.shape
+        Ho, Wo = H + 2 * pad - dil * (k - 1), W + 2 * pad - dil * (k - 1)
+        w = weight.detach().reshape(C, k * k).float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        y = _empty_nhwc(N, C, Ho, Wo, x)
+        _abi.check(_abi.lib().kdcc_dw_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), N, H, W, C, k, dil, pad,
+                                          _dtype_code(x), _stream()), "kdcc_dw_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.geom = (k, dil, pad, bias is not None, weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        k, dil, pad, has_bias, wshape = ctx.geom
+        N, C, H, W = x.shape
+        dy = _nhwc(dy)
+        need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+        dx = _empty_nhwc(N, C, H, W, x) if need_dx else None
+        dw = torch.empty((C, k * k), dtype=torch.float32, device=x.device) if need_dw else None
+        db = torch.empty((C,), dtype=torch.float32, device=x.device) if need_db else None
+        L = _abi.lib()
+        code = _dtype_code(x)
+        ws = _workspace(L.kdcc_dw_bwd_workspace_bytes(N, H, W, C, k, dil, pad, code), x.device)
+        _abi.check(L.kdcc_dw_bwd(_ptr(x), _ptr(w), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), ws.numel(),
+                                 N, H, W, C, k, dil, pad, code, _stream()), "kdcc_dw_bwd")
+        return dx, (dw.reshape(wshape) if need_dw else None), db, None, None, None
+
+
+def depthwise_conv(x, weight, bias, kernel_size, dilation, padding):
+    """F.conv2d(x, weight (C,1,k,k), bias, stride=1, padding, dilation, groups=C) on libkdcc."""
+    return _DepthwiseConv.apply(x, weight, bias, int(kernel_size), int(dilation), int(padding))
+
+
+# ---------------------------------------------------------------------------------------------------
+# pointwise
+# ---------------------------------------------------------------------------------------------------
+class _PointwiseConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, scale, shift, relu):
+        _require_cuda(x, weight, bias)
+        x = _nhwc(x)
+        N, K, H, W = x.shape
+        Co = weight.shape[0]
+        M = N * H * W
+        w = cast_weight(weight.detach().reshape(Co, K), x.dtype)
+        y = _empty_nhwc(N, Co, H, W, x)
+        fused = scale is not None or shift is not None or relu
+        eff_shift = shift
+        if bias is not None and not fused:
+            eff_shift = bias.detach().float().contiguous()
+        elif bias is not None:
+            raise _abi.KdccError("conv bias together with a fused BN epilogue is not supported; fold the bias into shift")
+        use_act = fused or bias is not None
+        _abi.check(_abi.lib().kdcc_pw_fwd(_ptr(x), _ptr(w), _ptr(scale), _ptr(eff_shift), int(bool(relu)),
+                                          None if use_act else _ptr(y), _ptr(y) if use_act else None,
+                                          M, K, Co, _dtype_code(x), _stream()), "kdcc_pw_fwd")
+        if fused:
+            ctx.mark_non_differentiable(y)  # inference-only epilogue (eval-mode BN fold)
+        ctx.save_for_backward(x, w)
+        ctx.meta = (bias is not None, weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        has_bias, wshape = ctx.meta
+        N, K, H, W = x.shape
+        Co = w.shape[0]
+        M = N * H * W
+        dy = _nhwc(dy)
+        L = _abi.lib()
+        code = _dtype_code(x)
+        st = _stream()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _empty_nhwc(N, K, H, W, x)
+            _abi.check(L.kdcc_pw_bwd_dx(_ptr(dy), _ptr(w), _ptr(dx), None, 0, M, K, Co, code, st), "kdcc_pw_bwd_dx")
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((Co, K), dtype=torch.float32, device=x.device)
+            ws = _workspace(L.kdcc_pw_bwd_workspace_bytes(1, M, K, Co, code), x.device)
+            _abi.check(L.kdcc_pw_bwd_dw(_ptr(dy), _ptr(x), _ptr(dw), _ptr(ws), ws.numel(), M, K, Co, code, st),
+                       "kdcc_pw_bwd_dw")
+            dw = dw.reshape(wshape)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty((Co,), dtype=torch.float32, device=x.device)
+            ws = _workspace(L.kdcc_colsum_workspace_bytes(M, Co), x.device)
+            _abi.check(L.kdcc_colsum(_ptr(dy), _ptr(db), _ptr(ws), ws.numel(), M, Co, code, st), "kdcc_colsum")
+        return dx, dw, db, None, None, None
+
+
+def pointwise_conv(x, weight, bias=None, scale=None, shift=None, relu=False):
+    """F.conv2d(x, weight (Co,C,1,1), bias) on libkdcc; optional fused eval-mode BN (scale, shift) + ReLU."""
+    return _PointwiseConv.apply(x, weight, bias, scale, shift, bool(relu))
+
+
+# ---------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------
+def _logit_strides(t):
+    """(N, C, HW, batch_stride, class_stride, pixel_stride) of a (N,C,*spatial) tensor, or None."""
+    N, C = t.shape[0], t.shape[1]
+    HW = 1
+    for d in t.shape[2:]:
+        HW *= d
+    if t.is_contiguous():
+        return N, C, HW, C * HW, HW, 1
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return N, C, HW, HW * C, 1, C
+    return None
+
+
+class _KdLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, t, temperature, target_is_prob):
+        _require_cuda(s, t)
+        if s.shape != t.shape or s.dim() < 2:
+            raise _abi.KdccError("kd loss expects matching (N, C, ...) tensors, got %s and %s" % (tuple(s.shape), tuple(t.shape)))
+        s = s.detach()
+        if s.dim() == 4 and s.is_contiguous(memory_format=torch.channels_last) and not s.is_contiguous():
+            fmt = torch.channels_last
+        else:
+            fmt = torch.contiguous_format
+            s = s.contiguous()
+        t = t.detach().to(s.dtype).contiguous(memory_format=fmt)
+        geo = _logit_strides(s)
+        N, C, HW, bs, cs, ps = geo
+        need_grad = ctx.needs_input_grad[0]
+        ds = torch.empty_like(s) if need_grad else None
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        L = _abi.lib()
+        ws = _workspace(L.kdcc_loss_workspace_bytes(), s.device)
+        _abi.check(L.kdcc_kd_loss(_ptr(s), _ptr(t), _ptr(ds), _ptr(loss), _ptr(ws), ws.numel(), N, C, HW, bs, cs, ps,
+                                  float(temperature), int(bool(target_is_prob)), _dtype_code(s), 1.0, _stream()),
+                   "kdcc_kd_loss")
+        ctx.ds = ds
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        ds = ctx.ds
+        if ds is None:
+            return None, None, None, None
+        g = g.detach().float().contiguous()
+        _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
+                   "kdcc_scale_inplace")
+        ctx.ds = None
+        return ds, None, None, None
+
+
+def kd_loss(inputs, targets, temperature=1.0, target_is_prob=False):
+    """T^2/(N*HW) * sum_pix KL(p_t || softmax(inputs/T)); fp32 0-dim tensor with grad_fn."""
+    return _KdLoss.apply(inputs, targets, float(temperature), bool(target_is_prob))
+
+
+class _HintLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, t, weight, scale):
+        _require_cuda(s, t, weight)
+        if s.shape != t.shape or s.dim() < 2:
+            raise _abi.KdccError("hint loss expects matching (N, C, ...) tensors, got %s and %s" % (tuple(s.shape), tuple(t.shape)))
+        s = s.detach()
+        N, C = s.shape[0], s.shape[1]
+        HW = s.numel() // max(N * C, 1)
+        if s.dim() == 4 and s.is_contiguous(memory_format=torch.channels_last) and not s.is_contiguous():
+            layout = _abi.NHWC
+            t = t.detach().to(s.dtype).contiguous(memory_format=torch.channels_last)
+        else:
+            layout = _abi.NCHW
+            s = s.contiguous()
+            t = t.detach().to(s.dtype).contiguous()
+        w = None
+        per_sample = 0
+        if weight is not None:
+            w = weight.detach().float().contiguous()
+            if w.dim() == 2 and w.shape == (N, C):
+                per_sample = 1
+            elif w.numel() != C:
+                raise _abi.KdccError("filter_weight must have shape (C,) or (N, C)")
+        need_grad = ctx.needs_input_grad[0]
+        ds = torch.empty_like(s) if need_grad else None
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        L = _abi.lib()
+        ws = _workspace(L.kdcc_loss_workspace_bytes() + 4 * N * C, s.device)
+        _abi.check(L.kdcc_hint_loss(_ptr(s), _ptr(t), _ptr(w), per_sample, _ptr(ds), _ptr(loss), _ptr(ws), ws.numel(),
+                                    N, C, HW, layout, float(scale), _dtype_code(s), 1.0, _stream()), "kdcc_hint_loss")
+        ctx.ds = ds
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        ds = ctx.ds
+        if ds is None:
+            return None, None, None, None
+        g = g.detach().float().contiguous()
+        _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
+                   "kdcc_scale_inplace")
+        ctx.ds = None
+        return ds, None, None, None
+
+
+def hint_loss(inputs, targets, filter_weight=None, scale=1.0):
+    """scale/N * sum_n [sum_c w mean_hw (s-t)^2 / sum_c w]; filter_weight None = uniform (MSELoss)."""
+    return _HintLoss.apply(inputs, targets, filter_weight, float(scale))

@@ -1,0 +1,56 @@
+"""Teacher->student distillation losses on libkdcc: same class names, constructor arguments and
+call signatures as the reference's `losses` package, so `getattr(losses, cfg['kd_loss']['type'])(**args)`
+(parse_config.py:89-93, train.py:48-50) keeps working.  Each forward is ONE fused kernel pass that
+also emits the gradient; the result is a 0-dim fp32 tensor with a grad_fn.
+"""
+from torch import nn
+
+from . import functional as F_kdcc
+
+
+class KLDivergenceLoss(nn.Module):
+    """losses/KLDiv.py:4-23 -- kl_div(log_softmax(s/T), softmax(t/T)) * T^2 * C, 'mean' over all elements."""
+
+    def __init__(self, temperature=1):
+        super().__init__()
+        self.temperature = temperature
+
+    def forward(self, inputs, targets):
+        return F_kdcc.kd_loss(inputs, targets, self.temperature, target_is_prob=False)
+
+
+class EnsembleKLDivergenceLoss(nn.Module):
+    """losses/EnsembleKLDiv.py:5-22 -- targets are already probabilities (soft ensemble prediction)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, inputs, targets):
+        return F_kdcc.kd_loss(inputs, targets, 1.0, target_is_prob=True)
+
+
+class MSELoss(nn.Module):
+    """losses/MSELoss.py:4-16 -- nn.MSELoss(reduction) * num_classes."""
+
+    def __init__(self, reduction='mean', num_classes=19):
+        super().__init__()
+        if reduction != 'mean':
+            raise ValueError("kdcc MSELoss implements reduction='mean' (the only value the reference configs use)")
+        self.reduction = reduction
+        self.num_classes = num_classes
+
+    def forward(self, inputs, targets):
+        return F_kdcc.hint_loss(inputs, targets, None, scale=float(self.num_classes))
+
+
+class WeightedHintMSELoss(nn.Module):
+    """losses/WeightedHintMSELoss.py:5-16 -- per-channel weighted spatial-mean squared difference.
+    `reduction` / `num_classes` are stored and unused, exactly as in the reference."""
+
+    def __init__(self, reduction='mean', num_classes=19):
+        super().__init__()
+        self.reduction = reduction
+        self.num_classes = num_classes
+
+    def forward(self, inputs, targets, filter_weight):
+        return F_kdcc.hint_loss(inputs, targets, filter_weight, scale=1.0)

@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C ABI, libkdcc.so) against the CPU oracle and the
+fixtures frozen from the reference modules.  Tolerances are BASELINE.json's: 1e-5 relative in fp32,
+2e-2 in bf16, measured as max|a-b| / max|b| per tensor."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2}
+BLOCK_CASES = ["cifar_k3", "city_k9d5", "ragged_k3d2", "k5", "shrink_k3p0", "onepix_k1"]
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def to_dev(a, dtype, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dtype)
+    if t.dim() == 4:
+        t = t.contiguous(memory_format=torch.channels_last)
+    return t.requires_grad_(grad)
+
+
+def host(t):
+    return t.detach().float().cpu().numpy()
+
+
+def q(a, dtype):
+    """Quantise a float32 array the way the device tensor will be (so the oracle sees the same inputs)."""
+    return host(torch.from_numpy(np.ascontiguousarray(a)).to(dtype))
+
+
+def run_block(kdcc, x, w_dw, w_pw, dy, k, d, p, dtype):
+    Ci, Co = w_dw.shape[0], w_pw.shape[0]
+    blk = kdcc.DepthwiseSeparableBlock(Ci, Co, k, p, d, Ci, None).cuda()
+    with torch.no_grad():
+        blk.separable_conv.weight.copy_(torch.from_numpy(w_dw))
+        blk.pointwise_conv.weight.copy_(torch.from_numpy(w_pw))
+    xt = to_dev(x, dtype, grad=True)
+    y = blk(xt)
+    y.backward(to_dev(dy, dtype))
+    torch.cuda.synchronize()
+    return host(y), host(xt.grad), host(blk.separable_conv.weight.grad), host(blk.pointwise_conv.weight.grad)
+
+
+@pytest.fixture(scope="module")
+def kdcc():
+    import kdcc as pkg
+    pkg._abi.lib()  # fails loudly when libkdcc.so is missing
+    return pkg
+
+
+@pytest.mark.parametrize("tag", BLOCK_CASES)
+def test_block_fp32_matches_reference_golden(kdcc, golden_block, tag):
+    g = golden_block
+    N, Ci, Co, H, W, k, d, p = [int(v) for v in g[f"{tag}/geom"]]
+    y, dx, dwd, dwp = run_block(kdcc, g[f"{tag}/x"], g[f"{tag}/w_dw"], g[f"{tag}/w_pw"], g[f"{tag}/dy"], k, d, p,
+                                torch.float32)
+    assert y.shape == g[f"{tag}/y"].shape
+    for name, mine in (("y", y), ("dx", dx), ("dw_dw", dwd), ("dw_pw", dwp)):
+        assert relerr(mine, g[f"{tag}/{name}"]) < TOL[torch.float32], name
+
+
+@pytest.mark.parametrize("mode", ["tma", "tma_plain_load", "tma_plain_store", "direct"])
+@pytest.mark.parametrize("tag", BLOCK_CASES)
+def test_block_bf16_matches_reference_golden(kdcc, golden_block, tag, mode, monkeypatch):
+    monkeypatch.setenv("KDCC_DW_MODE", {"tma": "0", "tma_plain_load": "1", "tma_plain_store": "2", "direct": "0"}[mode])
+    monkeypatch.setenv("KDCC_DW_FORCE_DIRECT", "1" if mode == "direct" else "0")
+    g = golden_block
+    N, Ci, Co, H, W, k, d, p = [int(v) for v in g[f"{tag}/geom"]]
+    y, dx, dwd, dwp = run_block(kdcc, g[f"{tag}/x"], g[f"{tag}/w_dw"], g[f"{tag}/w_pw"], g[f"{tag}/dy"], k, d, p,
+                                torch.bfloat16)
+    for name, mine in (("y", y), ("dx", dx), ("dw_dw", dwd), ("dw_pw", dwp)):
+        assert relerr(mine, g[f"{tag}/{name}"]) < TOL[torch.bfloat16], name
+
+
+def oracle_block(x, w_dw, w_pw, dy, k, d, p, dtype):
+    """Oracle on inputs quantised like the device tensors; the intermediate is re-quantised too (bf16 path)."""
+    from oracle import oracle as orc
+    xq, dyq = q(x, dtype), q(dy, dtype)
+    wpq = q(w_pw, dtype)
+    mid = q(orc.dw_fwd(xq, w_dw, k, d, p), dtype)
+    y = orc.pw_fwd(mid, wpq)
+    dmid, dwp, _ = orc.pw_bwd(mid, wpq, dyq)
+    dx, dwd, _ = orc.dw_bwd(xq, w_dw, q(dmid, dtype), k, d, p)
+    return y, dx, dwd, dwp
+
+
+SEEDED = [
+    # N, Ci, Co,  H,  W, k, d,  p
+    (2, 64, 128, 40, 40, 9, 5, 20),    # Cityscapes geometry, several 26x26 sub-image tiles
+    (1, 32, 64, 131, 67, 9, 5, 20),    # ragged: residues with unequal sub-image sizes, partial tiles
+    (2, 32, 64, 33, 47, 3, 1, 1),      # 3x3, ragged edges
+    (3, 16, 8, 20, 20, 3, 2, 2),       # dilated 3x3
+    (32, 64, 64, 8, 8, 3, 1, 1),       # CIFAR ResNet44 layer3 block shape
+    (1, 384, 384, 32, 32, 9, 5, 20),   # HRNet-OCR site shape
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("geom", SEEDED)
+def test_block_matches_oracle_seeded(kdcc, geom, dtype):
+    N, Ci, Co, H, W, k, d, p = geom
+    rs = np.random.RandomState(1234 + Ci + H)
+    x = rs.standard_normal((N, Ci, H, W)).astype(np.float32)
+    w_dw = (rs.uniform(-1, 1, (Ci, 1, k, k)) / k).astype(np.float32)
+    w_pw = (rs.uniform(-1, 1, (Co, Ci, 1, 1)) / np.sqrt(Ci)).astype(np.float32)
+    Ho, Wo = H + 2 * p - d * (k - 1), W + 2 * p - d * (k - 1)
+    dy = rs.standard_normal((N, Co, Ho, Wo)).astype(np.float32)
+    y, dx, dwd, dwp = run_block(kdcc, x, w_dw, w_pw, dy, k, d, p, dtype)
+    ry, rdx, rdwd, rdwp = oracle_block(x, w_dw, w_pw, dy, k, d, p, dtype)
+    for name, mine, ref in (("y", y, ry), ("dx", dx, rdx), ("dw_dw", dwd, rdwd), ("dw_pw", dwp, rdwp)):
+        assert relerr(mine, ref) < TOL[dtype], name
+
+
+GEMMS = [(4096, 512, 512), (2048, 1024, 2048), (1024, 4096, 256), (2000, 72, 24), (128 * 5 + 8, 64, 64), (300, 384, 384)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mkn", GEMMS)
+def test_pointwise_gemm_matches_oracle(kdcc, mkn, dtype):
+    from oracle import oracle as orc
+    M, K, Nc = mkn
+    rs = np.random.RandomState(M + K)
+    x = q(rs.standard_normal((1, K, M, 1)).astype(np.float32), dtype)
+    w = q((rs.uniform(-1, 1, (Nc, K, 1, 1)) / np.sqrt(K)).astype(np.float32), dtype)
+    dy = q(rs.standard_normal((1, Nc, M, 1)).astype(np.float32), dtype)
+    xt = to_dev(x, dtype, grad=True)
+    wt = torch.from_numpy(w).cuda().requires_grad_(True)
+    y = kdcc.functional.pointwise_conv(xt, wt)
+    y.backward(to_dev(dy, dtype))
+    torch.cuda.synchronize()
+    ry = orc.pw_fwd(x, w)
+    rdx, rdw, _ = orc.pw_bwd(x, w, dy)
+    assert relerr(host(y), ry) < TOL[dtype]
+    assert relerr(host(xt.grad), rdx) < TOL[dtype]
+    assert relerr(host(wt.grad), rdw) < TOL[dtype]
+
+
+def test_pointwise_fused_bn_relu_epilogue(kdcc):
+    from oracle import oracle as orc
+    rs = np.random.RandomState(5)
+    M, K, Nc = 1024, 256, 512
+    x = q(rs.standard_normal((1, K, M, 1)).astype(np.float32), torch.bfloat16)
+    w = q((rs.uniform(-1, 1, (Nc, K, 1, 1)) / np.sqrt(K)).astype(np.float32), torch.bfloat16)
+    scale = rs.uniform(0.5, 1.5, Nc).astype(np.float32)
+    shift = rs.uniform(-0.5, 0.5, Nc).astype(np.float32)
+    with torch.no_grad():
+        y = kdcc.functional.pointwise_conv(to_dev(x, torch.bfloat16), torch.from_numpy(w).cuda(), None,
+                                           torch.from_numpy(scale).cuda(), torch.from_numpy(shift).cuda(), True)
+    ref = np.maximum(orc.pw_fwd(x, w) * scale[None, :, None, None] + shift[None, :, None, None], 0)
+    assert relerr(host(y), ref) < TOL[torch.bfloat16]
+
+
+# ---- losses ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("tag", ["kl_T1", "kl_T2", "kl_T5", "kl_big", "kl_cifar_T5"])
+def test_kd_loss_golden(kdcc, golden_losses, tag, dtype):
+    from oracle import oracle as orc
+    g = golden_losses
+    T = float(g[f"{tag}/T"])
+    s = to_dev(g[f"{tag}/arg0"], dtype, grad=True)
+    t = to_dev(g[f"{tag}/arg1"], dtype)
+    loss = kdcc.KLDivergenceLoss(temperature=T)(s, t)
+    loss.backward()
+    if dtype == torch.float32:
+        ref_loss, ref_grad = float(g[f"{tag}/loss"]), g[f"{tag}/grad"]
+    else:  # oracle on the bf16-rounded logits
+        ref_loss, ref_grad = orc.kd_loss(q(g[f"{tag}/arg0"], dtype), q(g[f"{tag}/arg1"], dtype), T=T)
+    assert abs(float(loss) - ref_loss) <= TOL[dtype] * abs(ref_loss)
+    assert relerr(host(s.grad), ref_grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_kd_loss_layouts_and_no_grad(kdcc, golden_losses, layout):
+    g, tag = golden_losses, "kl_T2"
+    s = torch.from_numpy(g[f"{tag}/arg0"]).cuda()
+    t = torch.from_numpy(g[f"{tag}/arg1"]).cuda()
+    if layout == "nhwc":
+        s, t = s.contiguous(memory_format=torch.channels_last), t.contiguous(memory_format=torch.channels_last)
+    s.requires_grad_(True)
+    loss = kdcc.KLDivergenceLoss(temperature=2)(s, t)
+    (loss * 0.25).backward()  # upstream scalar is applied by kdcc_scale_inplace
+    assert abs(float(loss) - float(g[f"{tag}/loss"])) <= 1e-5 * abs(float(g[f"{tag}/loss"]))
+    assert relerr(host(s.grad), 0.25 * g[f"{tag}/grad"]) < 1e-5
+    with torch.no_grad():
+        l2 = kdcc.KLDivergenceLoss(temperature=2)(s, t)
+    assert not l2.requires_grad and float(l2) == float(loss)
+
+
+@pytest.mark.parametrize("tag", ["ekl", "ekl_onehot"])
+def test_ensemble_kd_loss_golden(kdcc, golden_losses, tag):
+    g = golden_losses
+    s = to_dev(g[f"{tag}/arg0"], torch.float32, grad=True)
+    loss = kdcc.EnsembleKLDivergenceLoss()(s, to_dev(g[f"{tag}/arg1"], torch.float32))
+    loss.backward()
+    assert abs(float(loss) - float(g[f"{tag}/loss"])) <= 1e-5 * abs(float(g[f"{tag}/loss"]))
+    assert relerr(host(s.grad), g[f"{tag}/grad"]) < 1e-5
+
+
+def test_kd_loss_many_classes_generic_kernel(kdcc):
+    from oracle import oracle as orc
+    rs = np.random.RandomState(3)
+    s = rs.standard_normal((16, 100)).astype(np.float32) * 3   # CIFAR-100 sized class axis
+    t = rs.standard_normal((16, 100)).astype(np.float32) * 3
+    st = torch.from_numpy(s).cuda().requires_grad_(True)
+    loss = kdcc.KLDivergenceLoss(temperature=4)(st, torch.from_numpy(t).cuda())
+    loss.backward()
+    rl, rg = orc.kd_loss(s, t, T=4.0)
+    assert abs(float(loss) - rl) <= 1e-5 * abs(rl)
+    assert relerr(host(st.grad), rg) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("tag", ["whint_vec", "whint_tab", "mse_nc1000", "mse_nc1", "mse_1x1"])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_hint_losses_golden(kdcc, golden_losses, tag, dtype, layout):
+    from oracle import oracle as orc
+    g = golden_losses
+    s_np, t_np = g[f"{tag}/arg0"], g[f"{tag}/arg1"]
+    s = torch.from_numpy(s_np).cuda().to(dtype)
+    t = torch.from_numpy(t_np).cuda().to(dtype)
+    if layout == "nhwc":
+        s, t = s.contiguous(memory_format=torch.channels_last), t.contiguous(memory_format=torch.channels_last)
+    s.requires_grad_(True)
+    if tag.startswith("whint"):
+        w_np = g[f"{tag}/arg2"]
+        loss = kdcc.WeightedHintMSELoss()(s, t, torch.from_numpy(w_np).cuda())
+        ref_loss, ref_grad = orc.hint_loss(q(s_np, dtype), q(t_np, dtype), w=w_np, scale=1.0)
+    else:
+        nc = float(g[f"{tag}/nc"])
+        loss = kdcc.MSELoss(num_classes=nc)(s, t)
+        ref_loss, ref_grad = orc.hint_loss(q(s_np, dtype), q(t_np, dtype), w=None, scale=nc)
+    loss.backward()
+    if dtype == torch.float32:
+        ref_loss, ref_grad = float(g[f"{tag}/loss"]), g[f"{tag}/grad"]
+    assert abs(float(loss) - ref_loss) <= TOL[dtype] * abs(ref_loss)
+    assert relerr(host(s.grad), ref_grad) < TOL[dtype]
+
+
+# ---- BASELINE-size properties (no oracle: size-independent identities) -------------------------------
+def test_full_size_depthwise_impulse_and_linearity(kdcc):
+    """1024^2 crop -> 128x128 maps, C=512, k=9 d=5 p=20: an impulse reproduces the (mirrored) taps, and the
+    conv is linear in x."""
+    torch.manual_seed(0)
+    C, H, W, k, d, p = 512, 128, 128, 9, 5, 20
+    w = torch.randn(C, 1, k, k, device="cuda")
+    x = torch.zeros(1, C, H, W, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x[0, :, 64, 70] = 1.0
+    y = kdcc.functional.depthwise_conv(x, w, None, k, d, p).float()
+    # y[i,j] = w[u,v] where (64,70) = (i + u*d - p, j + v*d - p)
+    expect = torch.zeros(1, C, H, W, device="cuda")
+    for u in range(k):
+        for v in range(k):
+            i, j = 64 - u * d + p, 70 - v * d + p
+            if 0 <= i < H and 0 <= j < W:
+                expect[0, :, i, j] = w[:, 0, u, v]
+    assert torch.allclose(y, expect.to(torch.bfloat16).float(), atol=0, rtol=0)
+    a = torch.randn(1, C, H, W, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y1 = kdcc.functional.depthwise_conv(a, w, None, k, d, p).float()
+    y2 = kdcc.functional.depthwise_conv(a * 2, w, None, k, d, p).float()
+    assert torch.equal(y2, 2 * y1)  # exact: scaling by 2 commutes with every rounding
+
+
+def test_full_size_depthwise_backward_adjoint(kdcc):
+    """<dw(x), g> == <x, dw^T(g)> and == sum(w * dW): the three kernels are mutually consistent at full size."""
+    torch.manual_seed(1)
+    C, H, W, k, d, p = 512, 128, 128, 9, 5, 20
+    w = (torch.randn(C, 1, k, k, device="cuda") / k).requires_grad_(True)
+    x = torch.randn(2, C, H, W, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    g = torch.randn(2, C, H, W, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = kdcc.functional.depthwise_conv(x, w, None, k, d, p)
+    y.backward(g)
+    lhs = (y.double() * g.double()).sum()
+    mid = (x.detach().double() * x.grad.double()).sum()
+    rhs = (w.detach().double() * w.grad.double()).sum()
+    assert abs(lhs - mid) / abs(lhs) < 1e-2
+    assert abs(lhs - rhs) / abs(lhs) < 1e-2
+
+
+def test_full_size_gemm_identity_and_colsum(kdcc):
+    """M = 16384 pixels, 512 -> 512: identity weights reproduce x bit-exactly; dW against dy = 1 is the column sum."""
+    torch.manual_seed(2)
+    M, K = 16384, 512
+    x = torch.randn(1, K, 128, 128, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = torch.eye(K, device="cuda").reshape(K, K, 1, 1).requires_grad_(True)
+    y = kdcc.functional.pointwise_conv(x, w)
+    assert torch.equal(y, x.detach())
+    y.backward(torch.ones_like(y))
+    colsum = x.detach().float().sum(dim=(0, 2, 3))
+    assert torch.allclose(w.grad.reshape(K, K), colsum[None, :].expand(K, K), rtol=1e-3, atol=1e-2)
+    assert torch.equal(x.grad.float(), torch.ones_like(x.grad).float())
+
+
+def test_full_size_losses_zero_at_equality_and_deterministic(kdcc):
+    torch.manual_seed(3)
+    s = (3 * torch.randn(1, 19, 1024, 1024, device="cuda")).requires_grad_(True)
+    l0 = kdcc.KLDivergenceLoss(temperature=5)(s, s.detach().clone())
+    l0.backward()
+    assert abs(float(l0)) < 1e-6 and float(s.grad.abs().max()) < 1e-9
+    t = 3 * torch.randn(1, 19, 1024, 1024, device="cuda")
+    a = kdcc.KLDivergenceLoss(temperature=5)(s, t)
+    b = kdcc.KLDivergenceLoss(temperature=5)(s, t)
+    assert float(a) == float(b) and float(a) > 0      # fixed-order reduction: bit-reproducible
+    # gradient of each pixel sums to zero over classes
+    s.grad = None
+    a.backward()
+    assert float(s.grad.sum(dim=1).abs().max()) < 1e-9
+    f = torch.randn(1, 512, 128, 128, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    h0 = kdcc.MSELoss(num_classes=1000)(f, f.detach().clone())
+    assert float(h0) == 0.0
+    tt = torch.randn_like(f)
+    h1 = kdcc.MSELoss(num_classes=1000)(f, tt)
+    ref = torch.nn.functional.mse_loss(f.detach().float(), tt.float()) * 1000
+    assert abs(float(h1) - float(ref)) / float(ref) < 1e-4
+
+
+def test_errors_are_loud(kdcc):
+    with pytest.raises(kdcc.KdccError):
+        kdcc.functional.depthwise_conv(torch.randn(1, 8, 4, 4), torch.randn(8, 1, 3, 3), None, 3, 1, 1)  # CPU tensor
+    with pytest.raises(kdcc.KdccError):  # 6 channels: not a 16-byte vector -> KDCC_ESHAPE, no fallback
+        kdcc.functional.depthwise_conv(torch.randn(1, 6, 4, 4, device="cuda"), torch.randn(6, 1, 3, 3, device="cuda"), None, 3, 1, 1)
+    with pytest.raises(RuntimeError):    # reference behaviour: a Tensor bias is rejected by nn.Conv2d
+        kdcc.DepthwiseSeparableBlock(8, 8, 3, 1, 1, 8, torch.zeros(8))
