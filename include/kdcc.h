@@ -45,6 +45,8 @@ typedef void *kdcc_stream_t; /* cudaStream_t */
 
 int kdcc_version(void);
 const char *kdcc_strerror(int code);
+/* CUresult of the calling thread's most recent TMA-descriptor encode (0 = CUDA_SUCCESS); diagnostics only. */
+int kdcc_last_driver_status(void);
 
 /* Which implementation a call would dispatch to (for tests / profiles): returns a static string such
  * as "dw_fwd_tma_k9" or "dw_fwd_direct".  op: 0 = dw_fwd, 1 = dw_bwd, 2 = pw_fwd, 3 = pw_bwd_dx,

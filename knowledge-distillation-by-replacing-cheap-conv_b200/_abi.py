@@ -18,6 +18,7 @@ _vp, _i, _l, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_fl
 SIGNATURES = {
     "kdcc_version": (_i, []),
     "kdcc_strerror": (ctypes.c_char_p, [_i]),
+    "kdcc_last_driver_status": (_i, []),
     "kdcc_dispatch_name": (ctypes.c_char_p, [_i] * 10),
     "kdcc_dw_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "kdcc_dw_bwd_workspace_bytes": (_sz, [_i] * 8),
@@ -65,7 +66,10 @@ def strerror(code):
 
 def check(code, what):
     if code != 0:
-        raise KdccError("%s failed: %s (code %d)" % (what, strerror(code), code))
+        extra = ""
+        if code == -2 and lib().kdcc_last_driver_status() != 0:
+            extra = " [TMA descriptor encode returned CUresult %d]" % lib().kdcc_last_driver_status()
+        raise KdccError("%s failed: %s (code %d)%s" % (what, strerror(code), code, extra))
 
 
 def dispatch_name(op, N, H, W, C, Cout, k, dil, pad, dtype):

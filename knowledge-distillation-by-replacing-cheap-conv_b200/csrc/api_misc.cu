@@ -1,10 +1,13 @@
 // Version / error-string / dispatch-introspection entry points of the C ABI (include/kdcc.h).
 #include "dw_kernels.cuh"
 #include "pw_kernels.cuh"
+#include "sm100_ptx.cuh"
 
 using namespace kdcc;
 
 KDCC_API int kdcc_version(void) { return KDCC_VERSION; }
+
+KDCC_API int kdcc_last_driver_status(void) { return last_driver_status(); }
 
 KDCC_API const char *kdcc_strerror(int code) {
   switch (code) {

@@ -136,4 +136,6 @@ EncodeTiledFn get_encode_tiled();  // nullptr when the driver cannot provide it
 int make_tmap_bf16(CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
                    const uint32_t *box, const uint32_t *elem_strides, CUtensorMapSwizzle swizzle);
 
+int last_driver_status();  // CUresult of this thread's last descriptor encode (diagnostics)
+
 }  // namespace kdcc

@@ -1,0 +1,193 @@
+"""The distillation hot path as one fused, autograd-free pass over pre-allocated buffers.
+
+This is the body of the reference's layerwise training loop restricted to the rows SURVEY.md §8 puts on
+the path (trainer/layerwise_trainer.py:223-239): for every replaced site run the cheap-conv block
+forward, the hint loss against the teacher feature (which emits d loss / d y in the same pass),
+the block backward (pointwise dW + dX, depthwise dW + dX), then the logits KD loss, the student-gradient
+all-reduce and the optimizer step.  Every arithmetic step is a libkdcc.so call on raw pointers; torch
+only owns the memory, the stream, the NCCL all-reduce and the optimizer.
+
+`HotPathStep` is what bench.py times and what `LayerwiseStep` (trainer.py) uses for the loss side.
+"""
+import math
+
+import torch
+
+from . import _abi
+from .functional import _ptr, _stream
+
+# (C_in, C_out) of the sites replaced by the shipped Cityscapes plans, all on 128x128 maps for a 1024^2 crop
+PLAN_51M_DEEPLAB = [(512, 512)] * 5 + [(1024, 2048)] + [(4096, 256)] * 3      # cfg/cityscapes/51M_deeplab_all.json:123-160
+PLAN_58M_DEEPLAB = [(512, 512)] * 6 + [(512, 1024), (1024, 2048)] + [(4096, 256)] * 3  # cfg/cityscapes/58M_deeplab_all.json
+PLAN_CIFAR_RESNET44 = [(64, 64)] * 8                                           # cfg/cifar10/resnet44/config1.json
+
+
+class EventLog:
+    """CUDA-event timeline on the launching stream: one event after every kernel call."""
+
+    def __init__(self):
+        self.names, self.events = [], []
+
+    def mark(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        self.names.append(name)
+        self.events.append(ev)
+
+    def durations_ms(self):
+        """{name: [ms, ...]} -- each call's time is the gap to the previous mark ('begin' marks reset it)."""
+        out = {}
+        for i in range(1, len(self.events)):
+            if self.names[i] == "begin":
+                continue
+            out.setdefault(self.names[i], []).append(self.events[i - 1].elapsed_time(self.events[i]))
+        return out
+
+
+class HotPathStep:
+    def __init__(self, plan, batch, height, width, kernel_size=9, dilation=5, padding=20, dtype=torch.bfloat16,
+                 device="cuda", logits_shape=None, kd_temperature=1.0, hint_num_classes=1000.0,
+                 accumulation_steps=1, kd_grad=False, need_dx=True, seed=0):
+        self.plan = list(plan)
+        self.N, self.H, self.W = batch, height, width
+        self.k, self.d, self.p = kernel_size, dilation, padding
+        self.Ho = height + 2 * padding - dilation * (kernel_size - 1)
+        self.Wo = width + 2 * padding - dilation * (kernel_size - 1)
+        self.dtype, self.device = dtype, torch.device(device)
+        self.code = _abi.F32 if dtype == torch.float32 else _abi.BF16
+        self.T, self.nc, self.acc_steps = float(kd_temperature), float(hint_num_classes), int(accumulation_steps)
+        self.kd_grad, self.need_dx = kd_grad, need_dx
+        self.L = _abi.lib()
+        kk = kernel_size * kernel_size
+
+        # flat fp32 parameter / gradient buckets: [dw weights of site 0 | pw weights of site 0 | site 1 ...]
+        sizes = []
+        for ci, co in self.plan:
+            sizes += [ci * kk, co * ci]
+        total = sum(sizes)
+        gen = torch.Generator(device="cpu").manual_seed(seed)
+        flat = torch.empty(total, dtype=torch.float32)
+        off = 0
+        self._views = []
+        for (ci, co) in self.plan:
+            # nn.Conv2d default init bounds: U(+-1/sqrt(fan_in)), fan_in = k*k (depthwise) or C_in (pointwise)
+            flat[off:off + ci * kk].uniform_(-1.0 / kernel_size, 1.0 / kernel_size, generator=gen)
+            flat[off + ci * kk:off + ci * kk + co * ci].uniform_(-1.0 / math.sqrt(ci), 1.0 / math.sqrt(ci), generator=gen)
+            self._views.append((off, off + ci * kk, off + ci * kk + co * ci))
+            off += ci * kk + co * ci
+        self.flat_params = flat.to(self.device)
+        self.flat_grads = torch.zeros_like(self.flat_params)
+        self.num_trainable = total
+
+        cmax = max(ci for ci, _ in self.plan)
+        omax = max(co for _, co in self.plan)
+        n = batch
+        e = lambda c, h, w: torch.empty((n, h, w, c), dtype=dtype, device=self.device)
+        # scratch shared by all sites (each site's forward+backward completes before the next starts)
+        self.mid = e(cmax, self.Ho, self.Wo)
+        self.dmid = e(cmax, self.Ho, self.Wo)
+        self.dx = e(cmax, height, width) if need_dx else None
+        self.y = e(omax, self.Ho, self.Wo)
+        self.dy = e(omax, self.Ho, self.Wo)
+        self.w_pw_lp = torch.empty(max(co * ci for ci, co in self.plan), dtype=dtype, device=self.device)
+        ws_bytes = self.L.kdcc_loss_workspace_bytes()
+        for ci, co in self.plan:
+            M = n * self.Ho * self.Wo
+            ws_bytes = max(ws_bytes, self.L.kdcc_dw_bwd_workspace_bytes(n, height, width, ci, self.k, self.d, self.p, self.code),
+                           self.L.kdcc_pw_bwd_workspace_bytes(1, M, ci, co, self.code))
+        self.ws = torch.empty(ws_bytes + 64, dtype=torch.uint8, device=self.device)
+        self.hint_losses = torch.zeros(len(self.plan), dtype=torch.float32, device=self.device)
+        self.kd_loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.logits_shape = logits_shape
+        self.dlogits = torch.empty(logits_shape, dtype=torch.float32, device=self.device) if (logits_shape and kd_grad) else None
+        self.launches_per_step = 0
+
+    # ---- synthetic inputs of the right shapes (the frozen trunk that would produce them is out of scope) ----
+    def make_inputs(self, seed=1, pinned_host=False):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        dev = "cpu" if pinned_host else self.device
+
+        def rnd(shape, dtype, scale=1.0):
+            t = (torch.randn(shape, generator=g) * scale).to(dtype)
+            return t.pin_memory() if pinned_host else t.to(self.device)
+
+        xs = [rnd((self.N, self.H, self.W, ci), self.dtype) for ci, _ in self.plan]
+        ts = [rnd((self.N, self.Ho, self.Wo, co), self.dtype) for _, co in self.plan]
+        ls = lt = None
+        if self.logits_shape:
+            ls, lt = rnd(self.logits_shape, torch.float32, 3.0), rnd(self.logits_shape, torch.float32, 3.0)
+        return xs, ts, ls, lt
+
+    def _site_weights(self, i):
+        a, b, c = self._views[i]
+        return self.flat_params[a:b], self.flat_params[b:c], self.flat_grads[a:b], self.flat_grads[b:c]
+
+    def step(self, xs, teacher_feats, logits_s=None, logits_t=None, log=None):
+        """One pass; returns (hint_loss_sum, kd_loss) as 0-dim device tensors (no host sync)."""
+        L, st, code, n = self.L, _stream(), self.code, self.N
+        H, W, Ho, Wo, k, d, p = self.H, self.W, self.Ho, self.Wo, self.k, self.d, self.p
+        chk = _abi.check
+        ws, wsn = _ptr(self.ws), self.ws.numel()
+        mark = log.mark if log is not None else (lambda name: None)
+        launches = 0
+        mark("begin")
+        for i, (ci, co) in enumerate(self.plan):
+            w_dw, w_pw, g_dw, g_pw = self._site_weights(i)
+            x, tf = xs[i], teacher_feats[i]
+            M = n * Ho * Wo
+            w_lp = w_pw
+            if code == _abi.BF16:
+                w_lp = self.w_pw_lp[:co * ci]
+                chk(L.kdcc_cast_f32_to_bf16(_ptr(w_pw), _ptr(w_lp), co * ci, st), "cast")
+                mark("cast_w")
+                launches += 1
+            chk(L.kdcc_dw_fwd(_ptr(x), _ptr(w_dw), None, _ptr(self.mid), n, H, W, ci, k, d, p, code, st), "dw_fwd")
+            mark("dw_fwd")
+            chk(L.kdcc_pw_fwd(_ptr(self.mid), _ptr(w_lp), None, None, 0, _ptr(self.y), None, M, ci, co, code, st), "pw_fwd")
+            mark("pw_fwd")
+            chk(L.kdcc_hint_loss(_ptr(self.y), _ptr(tf), None, 0, _ptr(self.dy), _ptr(self.hint_losses[i:]), ws, wsn,
+                                 n, co, Ho * Wo, _abi.NHWC, self.nc, code, 1.0 / self.acc_steps, st), "hint_loss")
+            mark("hint_loss")
+            chk(L.kdcc_pw_bwd_dw(_ptr(self.dy), _ptr(self.mid), _ptr(g_pw), ws, wsn, M, ci, co, code, st), "pw_bwd_dw")
+            mark("pw_bwd_dw")
+            chk(L.kdcc_pw_bwd_dx(_ptr(self.dy), _ptr(w_lp), _ptr(self.dmid), None, 0, M, ci, co, code, st), "pw_bwd_dx")
+            mark("pw_bwd_dx")
+            chk(L.kdcc_dw_bwd(_ptr(x), _ptr(w_dw), _ptr(self.dmid), _ptr(self.dx) if self.need_dx else None, _ptr(g_dw),
+                              None, ws, wsn, n, H, W, ci, k, d, p, code, st), "dw_bwd")
+            mark("dw_bwd")
+            # dw_fwd 1, pw_fwd 1, hint 2 (pass + finalize), pw_dw 2 (gemm + split reduce), pw_dx 1,
+            # dw_bwd: wgrad 1 + reduce 1 (+ dx conv 1)
+            launches += 1 + 1 + 2 + 2 + 1 + (3 if self.need_dx else 2)
+        if logits_s is not None:
+            N_, C_ = logits_s.shape[0], logits_s.shape[1]
+            HW = logits_s.numel() // (N_ * C_)
+            chk(L.kdcc_kd_loss(_ptr(logits_s), _ptr(logits_t), _ptr(self.dlogits) if self.kd_grad else None,
+                               _ptr(self.kd_loss), ws, wsn, N_, C_, HW, C_ * HW, HW, 1, self.T, 0, _abi.F32,
+                               1.0 / self.acc_steps, st), "kd_loss")
+            mark("kd_loss")
+            launches += 2
+        self.launches_per_step = launches
+        return self.hint_losses.sum(), self.kd_loss
+
+    # ---- algorithmic work per step, used for the roofline figures -----------------------------
+    def algorithmic(self):
+        """{kernel: (bytes_or_flops_per_step, 'B'|'FLOP')} summed over the sites of one step."""
+        es = 4 if self.dtype == torch.float32 else 2
+        P_in, P_out, n, kk = self.H * self.W, self.Ho * self.Wo, self.N, self.k * self.k
+        out = {"dw_fwd": 0, "dw_bwd": 0, "pw_fwd": 0, "pw_bwd_dx": 0, "pw_bwd_dw": 0, "hint_loss": 0, "kd_loss": 0}
+        for ci, co in self.plan:
+            out["dw_fwd"] += n * (P_in + P_out) * ci * es + ci * kk * 4
+            out["dw_bwd"] += n * (P_in + P_out + (P_in if self.need_dx else 0)) * ci * es + ci * kk * 4
+            flops = 2 * n * P_out * ci * co
+            out["pw_fwd"] += flops
+            out["pw_bwd_dx"] += flops
+            out["pw_bwd_dw"] += flops
+            out["hint_loss"] += 3 * n * P_out * co * es
+        if self.logits_shape:
+            numel = 1
+            for s_ in self.logits_shape:
+                numel *= s_
+            out["kd_loss"] = (3 if self.kd_grad else 2) * numel * 4
+        units = {"dw_fwd": "B", "dw_bwd": "B", "hint_loss": "B", "kd_loss": "B",
+                 "pw_fwd": "FLOP", "pw_bwd_dx": "FLOP", "pw_bwd_dw": "FLOP"}
+        return {k_: (v, units[k_]) for k_, v in out.items()}
