@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4, help="images (1024^2 crops) per GPU per step")
     ap.add_argument("--crop", type=int, default=1024)
     ap.add_argument("--dw", default="k9d5p20", help="depthwise geometry kKdDpP (Cityscapes cfgs: k9d5p20; CIFAR: k3d1p1)")
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"],
+                    help="activation layout: nchw = the reference's (tensor-core depthwise), nhwc = channels_last kernels")
     ap.add_argument("--kd-grad", action="store_true", help="also emit d KD / d logits (ClassificationTrainer path)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,7 +218,7 @@ def run_kdcc(args, rank, world, local_rank):
     N = args.batch
     logits_shape = (N, 19, args.crop, args.crop)
     hp = HotPathStep(plan, N, maps, maps, k, d, p, dtype=torch.bfloat16, device=dev, logits_shape=logits_shape,
-                     kd_temperature=1.0, hint_num_classes=1000.0, accumulation_steps=1, kd_grad=args.kd_grad, seed=rank)
+                     kd_temperature=1.0, hint_num_classes=1000.0, accumulation_steps=1, kd_grad=args.kd_grad, seed=rank, layout=args.layout)
     xs, ts, ls, lt = hp.make_inputs(seed=100 + rank)
     param = torch.nn.Parameter(hp.flat_params)
     param.grad = hp.flat_grads
@@ -332,7 +334,7 @@ def run_kdcc(args, rank, world, local_rank):
             "config": {"workload": "%s hot path: %d cheap-conv sites (dw %s + pw GEMM) fwd+bwd, hint MSE x%d, KD loss on (N,19,%d,%d), "
                                    "grad all-reduce, RAdam; frozen trunk not run" % (PLAN_NAME, len(plan), args.dw, len(plan), args.crop, args.crop),
                        "global_batch": world * N, "per_gpu_batch": N, "crop": args.crop, "feature_maps": "%dx%d" % (maps, maps),
-                       "parallelism": "dp%d" % world, "trainable_params": hp.num_trainable,
+                       "parallelism": "dp%d" % world, "trainable_params": hp.num_trainable, "layout": args.layout,
                        "cache": "inputs larger than L2 (per-step working set of several GB >> 126 MB), no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": hp.launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,

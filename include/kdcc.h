@@ -12,7 +12,10 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
  *   - entry points are re-entrant and hold no thread-affine state (autograd calls backward from its
  *     own worker thread);
- *   - activations are NHWC-physical (torch.channels_last): x[n][h][w][c]; logits carry explicit strides;
+ *   - activations are either NHWC-physical (torch.channels_last, x[n][h][w][c]) or NCHW-physical (the
+ *     reference's own layout, x[n][c][h][w]); every conv entry point takes a `layout` argument and the two
+ *     layouts dispatch to different kernels (NCHW bf16 depthwise runs on the tensor cores); logits carry
+ *     explicit strides;
  *   - dtype: KDCC_F32 (parity path, 1e-5 relative) or KDCC_BF16 (production path, fp32 accumulate);
  *   - return 0 on success, a negative KDCC_E* code for bad arguments / unsupported shapes (there is
  *     NO CPU or library fallback), or a positive cudaError_t.  kdcc_strerror() names any of them.
@@ -27,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KDCC_VERSION 100 /* round 1 */
+#define KDCC_VERSION 101 /* round 1, layout-aware depthwise/pointwise */
 
 enum { KDCC_F32 = 0, KDCC_BF16 = 1 };
 enum { KDCC_LAYOUT_NHWC = 0, KDCC_LAYOUT_NCHW = 1 };
@@ -52,40 +55,44 @@ int kdcc_last_driver_status(void);
  * as "dw_fwd_tma_k9" or "dw_fwd_direct".  op: 0 = dw_fwd, 1 = dw_bwd, 2 = pw_fwd, 3 = pw_bwd_dx,
  * 4 = pw_bwd_dw. */
 const char *kdcc_dispatch_name(int op, int N, int H, int W, int C, int Cout, int k, int dil, int pad,
-                               int dtype);
+                               int layout, int dtype);
 
 /* ---- depthwise k x k, stride 1, zero padding, dilation `dil` -----------------------------------
  * Replaces self.separable_conv(x)  (models/students/transform_blocks/depthwise_separable_conv.py:7-8,12
  * -> F.conv2d groups=C).  x [N,H,W,C], w fp32 [C,k,k] (the (C,1,k,k) parameter, contiguous),
  * bias fp32 [C] or NULL, y [N,Ho,Wo,C] with Ho = H + 2*pad - dil*(k-1). */
 int kdcc_dw_fwd(const void *x, const float *w, const float *bias, void *y, int N, int H, int W, int C,
-                int k, int dil, int pad, int dtype, kdcc_stream_t stream);
+                int k, int dil, int pad, int layout, int dtype, kdcc_stream_t stream);
 
 /* Autograd backward of the call above (depthwise_separable_conv.py:12 under loss.backward(),
  * trainer/layerwise_trainer.py:235).  dx [N,H,W,C] (NULL: input needs no grad), dw fp32 [C,k,k]
  * (NULL: frozen), dbias fp32 [C] or NULL.  Deterministic two-stage reduction, no atomics. */
-size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, int dil, int pad, int dtype);
+size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, int dil, int pad, int layout,
+                                   int dtype);
 int kdcc_dw_bwd(const void *x, const float *w, const void *dy, void *dx, float *dw, float *dbias,
                 void *workspace, size_t workspace_bytes, int N, int H, int W, int C, int k, int dil,
-                int pad, int dtype, kdcc_stream_t stream);
+                int pad, int layout, int dtype, kdcc_stream_t stream);
 
 /* ---- pointwise 1x1 = GEMM ----------------------------------------------------------------------
- * Replaces self.pointwise_conv(x)  (depthwise_separable_conv.py:9,13).  x [M,K] (M = N*H*W pixels,
- * K = C_in), w [Nc,K] in the activation dtype (the (Co,C,1,1) parameter, cast by kdcc_cast_f32),
- * out[m][n] = sum_k x[m][k] w[n][k].  Optional fused epilogue on the second output:
+ * Replaces self.pointwise_conv(x)  (depthwise_separable_conv.py:9,13).  M = batch*H*W pixels, K = C_in,
+ * w [Nc,K] in the activation dtype (the (Co,C,1,1) parameter, cast by kdcc_cast_f32_to_bf16).
+ * layout NHWC: x [M,K], out [M,Nc], out[m][n] = sum_k x[m][k] w[n][k]  (batch ignored);
+ * layout NCHW: x [batch,K,M/batch], out [batch,Nc,M/batch], out_b = W . x_b  (bf16 tensor-core path only).
+ * Optional fused epilogue on the second output:
  *   y_act = relu?( out * scale[n] + shift[n] )   (eval-mode BN fold + ReLU, SURVEY.md F9;
  *   scale NULL -> 1, shift NULL -> 0; shift alone is the conv bias).
  * y_raw (the tensor the hint hook captures) and y_act may each be NULL, not both. */
 int kdcc_pw_fwd(const void *x, const void *w, const float *scale, const float *shift, int relu,
-                void *y_raw, void *y_act, long M, int K, int Nc, int dtype, kdcc_stream_t stream);
+                void *y_raw, void *y_act, long M, int K, int Nc, int batch, int layout, int dtype,
+                kdcc_stream_t stream);
 
 /* Autograd backward of the call above.  dx[m][k] = sum_n dy[m][n] w[n][k];
  * dw[n][k] = sum_m dy[m][n] x[m][k] (fp32 out, deterministic split-M reduction). */
 size_t kdcc_pw_bwd_workspace_bytes(int which /*0 = dx, 1 = dw*/, long M, int K, int Nc, int dtype);
 int kdcc_pw_bwd_dx(const void *dy, const void *w, void *dx, void *workspace, size_t workspace_bytes,
-                   long M, int K, int Nc, int dtype, kdcc_stream_t stream);
+                   long M, int K, int Nc, int batch, int layout, int dtype, kdcc_stream_t stream);
 int kdcc_pw_bwd_dw(const void *dy, const void *x, float *dw, void *workspace, size_t workspace_bytes,
-                   long M, int K, int Nc, int dtype, kdcc_stream_t stream);
+                   long M, int K, int Nc, int batch, int layout, int dtype, kdcc_stream_t stream);
 
 /* ---- losses ------------------------------------------------------------------------------------
  * kdcc_kd_loss replaces losses/KLDiv.py:19-23 (target_is_prob = 0) and losses/EnsembleKLDiv.py:18-22

@@ -19,14 +19,14 @@ SIGNATURES = {
     "kdcc_version": (_i, []),
     "kdcc_strerror": (ctypes.c_char_p, [_i]),
     "kdcc_last_driver_status": (_i, []),
-    "kdcc_dispatch_name": (ctypes.c_char_p, [_i] * 10),
-    "kdcc_dw_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "kdcc_dw_bwd_workspace_bytes": (_sz, [_i] * 8),
-    "kdcc_dw_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "kdcc_pw_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _l, _i, _i, _i, _vp]),
+    "kdcc_dispatch_name": (ctypes.c_char_p, [_i] * 11),
+    "kdcc_dw_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "kdcc_dw_bwd_workspace_bytes": (_sz, [_i] * 9),
+    "kdcc_dw_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "kdcc_pw_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp]),
     "kdcc_pw_bwd_workspace_bytes": (_sz, [_i, _l, _i, _i, _i]),
-    "kdcc_pw_bwd_dx": (_i, [_vp, _vp, _vp, _vp, _sz, _l, _i, _i, _i, _vp]),
-    "kdcc_pw_bwd_dw": (_i, [_vp, _vp, _vp, _vp, _sz, _l, _i, _i, _i, _vp]),
+    "kdcc_pw_bwd_dx": (_i, [_vp, _vp, _vp, _vp, _sz, _l, _i, _i, _i, _i, _i, _vp]),
+    "kdcc_pw_bwd_dw": (_i, [_vp, _vp, _vp, _vp, _sz, _l, _i, _i, _i, _i, _i, _vp]),
     "kdcc_loss_workspace_bytes": (_sz, []),
     "kdcc_kd_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _l, _l, _l, _l, _f, _i, _i, _f, _vp]),
     "kdcc_hint_loss": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _i, _l, _i, _f, _i, _f, _vp]),
@@ -72,5 +72,5 @@ def check(code, what):
         raise KdccError("%s failed: %s (code %d)%s" % (what, strerror(code), code, extra))
 
 
-def dispatch_name(op, N, H, W, C, Cout, k, dil, pad, dtype):
-    return lib().kdcc_dispatch_name(op, N, H, W, C, Cout, k, dil, pad, dtype).decode()
+def dispatch_name(op, N, H, W, C, Cout, k, dil, pad, layout, dtype):
+    return lib().kdcc_dispatch_name(op, N, H, W, C, Cout, k, dil, pad, layout, dtype).decode()

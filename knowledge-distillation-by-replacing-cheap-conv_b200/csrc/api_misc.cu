@@ -24,16 +24,23 @@ KDCC_API const char *kdcc_strerror(int code) {
 }
 
 KDCC_API const char *kdcc_dispatch_name(int op, int N, int H, int W, int C, int Cout, int k, int dil, int pad,
-                                        int dtype) {
-  (void)pad;
+                                        int layout, int dtype) {
   const bool bf16 = dtype == KDCC_BF16;
   const long M = (long)N * H * W;
+  const int Ho = H + 2 * pad - dil * (k - 1), Wo = W + 2 * pad - dil * (k - 1);
+  const bool nchw = layout == KDCC_LAYOUT_NCHW;
   switch (op) {
-    case 0: return bf16 && dw_tma_supported(C, k, dil) ? dw_tma_name(k, dil, 0) : "dw_direct";
-    case 1: return bf16 && dw_tma_supported(C, k, dil) ? dw_tma_name(k, dil, 1) : "dw_wgrad_direct";
-    case 2: return bf16 && pw_sm100_supported(M, C, Cout) ? "pw_gemm_sm100_tn" : "pw_simt";
-    case 3: return bf16 && pw_sm100_supported(M, C, Cout) ? "pw_gemm_sm100_dx" : "pw_simt";
-    case 4: return bf16 && pw_sm100_supported(M, C, Cout) ? "pw_gemm_sm100_dw" : "pw_simt";
+    case 0:
+      if (nchw) return bf16 && dw_tc_supported(H, W, Ho, Wo, k, dil) ? "dw_tc_conv" : "unsupported";
+      return bf16 && dw_tma_supported(C, k, dil) ? dw_tma_name(k, dil, 0) : "dw_direct";
+    case 1:
+      if (nchw) return bf16 && dw_tc_supported(H, W, Ho, Wo, k, dil) ? "dw_tc_wgrad" : "unsupported";
+      return bf16 && dw_tma_supported(C, k, dil) ? dw_tma_name(k, dil, 1) : "dw_wgrad_direct";
+    case 2: case 3: case 4: {
+      static const char *names[3] = {"pw_gemm_sm100_fwd", "pw_gemm_sm100_dx", "pw_gemm_sm100_dw"};
+      if (bf16 && pw_sm100_supported(M, C, Cout, N, layout)) return names[op - 2];
+      return nchw ? "unsupported" : "pw_simt";
+    }
     default: return "?";
   }
 }

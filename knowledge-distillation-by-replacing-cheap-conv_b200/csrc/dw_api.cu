@@ -1,46 +1,59 @@
 // C-ABI entry points for the depthwise convolution (declared in include/kdcc.h) and their dispatch:
-// bf16 shapes the TMA kernels cover -> dw_tma.cu, everything else (fp32 parity path, odd kernel sizes)
-// -> dw_direct.cu.  There is no CPU or library fallback: unsupported shapes return KDCC_ESHAPE.
+//   NCHW bf16                         -> tensor-core kernels (dw_tc.cu, dw_tc_wgrad.cu)
+//   NHWC bf16, k in {3, 9}, C % 16 == 0 -> TMA-staged CUDA-core kernels (dw_tma.cu)
+//   NHWC anything else (fp32 parity path, odd kernel sizes) -> direct kernels (dw_direct.cu)
+// There is no CPU or library fallback: unsupported combinations return KDCC_ESHAPE.
 #include <stdlib.h>
 
 #include "dw_kernels.cuh"
 
 using namespace kdcc;
 
+static bool env_flag(const char *name) {
+  const char *e = getenv(name);
+  return e && atoi(e);
+}
+
 static bool use_tma(int C, int k, int dil, int dtype) {
-  if (dtype != KDCC_BF16) return false;
-  const char *e = getenv("KDCC_DW_FORCE_DIRECT");
-  if (e && atoi(e)) return false;
+  if (dtype != KDCC_BF16 || env_flag("KDCC_DW_FORCE_DIRECT")) return false;
   return dw_tma_supported(C, k, dil);
 }
 
-static int check_geometry(int N, int H, int W, int C, int k, int dil, int pad, int dtype, int *Ho, int *Wo) {
+static int check_geometry(int N, int H, int W, int C, int k, int dil, int pad, int layout, int dtype, int *Ho, int *Wo) {
   if (N < 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || dil <= 0 || pad < 0) return KDCC_EINVAL;
   if (dtype != KDCC_F32 && dtype != KDCC_BF16) return KDCC_EINVAL;
+  if (layout != KDCC_LAYOUT_NHWC && layout != KDCC_LAYOUT_NCHW) return KDCC_EINVAL;
   *Ho = H + 2 * pad - dil * (k - 1);
   *Wo = W + 2 * pad - dil * (k - 1);
   if (*Ho <= 0 || *Wo <= 0) return KDCC_EINVAL;
-  if (C % (dtype == KDCC_F32 ? 4 : 8) != 0) return KDCC_ESHAPE;  // 16-byte channel vectors
+  if (layout == KDCC_LAYOUT_NHWC) {
+    if (C % (dtype == KDCC_F32 ? 4 : 8) != 0) return KDCC_ESHAPE;  // 16-byte channel vectors
+  } else {
+    if (dtype != KDCC_BF16 || !dw_tc_supported(H, W, *Ho, *Wo, k, dil)) return KDCC_ESHAPE;
+  }
   return KDCC_OK;
 }
 
 KDCC_API int kdcc_dw_fwd(const void *x, const float *w, const float *bias, void *y, int N, int H, int W, int C,
-                         int k, int dil, int pad, int dtype, kdcc_stream_t stream) {
+                         int k, int dil, int pad, int layout, int dtype, kdcc_stream_t stream) {
   int Ho, Wo;
-  int rc = check_geometry(N, H, W, C, k, dil, pad, dtype, &Ho, &Wo);
+  int rc = check_geometry(N, H, W, C, k, dil, pad, layout, dtype, &Ho, &Wo);
   if (rc) return rc;
   if (N == 0) return KDCC_OK;
   if (!x || !w || !y) return KDCC_EINVAL;
   if (!aligned16(x) || !aligned16(y)) return KDCC_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (layout == KDCC_LAYOUT_NCHW) return dw_tc_conv(x, w, bias, y, N, C, H, W, Ho, Wo, k, dil, pad, 0, st);
   if (use_tma(C, k, dil, dtype)) return dw_tma_conv(x, w, bias, y, N, H, W, C, Ho, Wo, k, dil, pad, 0, st);
   if (dtype == KDCC_F32) return dw_direct_fwd<float>(x, w, bias, y, N, H, W, C, Ho, Wo, k, dil, pad, 0, st);
   return dw_direct_fwd<__nv_bfloat16>(x, w, bias, y, N, H, W, C, Ho, Wo, k, dil, pad, 0, st);
 }
 
-KDCC_API size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, int dil, int pad, int dtype) {
+KDCC_API size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, int dil, int pad, int layout,
+                                            int dtype) {
   int Ho, Wo;
-  if (check_geometry(N, H, W, C, k, dil, pad, dtype, &Ho, &Wo) || N == 0) return 0;
+  if (check_geometry(N, H, W, C, k, dil, pad, layout, dtype, &Ho, &Wo) || N == 0) return 0;
+  if (layout == KDCC_LAYOUT_NCHW) return dw_tc_wgrad_workspace(N, C, Ho, Wo, k);
   const int vn = dtype == KDCC_F32 ? 4 : 8;
   size_t splits = (size_t)dw_direct_wgrad_splits(N, Ho, C, k, vn);
   if (dtype == KDCC_BF16 && dw_tma_supported(C, k, dil)) {
@@ -52,20 +65,30 @@ KDCC_API size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, i
 
 KDCC_API int kdcc_dw_bwd(const void *x, const float *w, const void *dy, void *dx, float *dw, float *dbias,
                          void *workspace, size_t workspace_bytes, int N, int H, int W, int C, int k, int dil,
-                         int pad, int dtype, kdcc_stream_t stream) {
+                         int pad, int layout, int dtype, kdcc_stream_t stream) {
   int Ho, Wo;
-  int rc = check_geometry(N, H, W, C, k, dil, pad, dtype, &Ho, &Wo);
+  int rc = check_geometry(N, H, W, C, k, dil, pad, layout, dtype, &Ho, &Wo);
   if (rc) return rc;
   if (N == 0) return KDCC_OK;
   if (!dy || (dx && !w) || ((dw || dbias) && (!x || !workspace))) return KDCC_EINVAL;
   if (!aligned16(dy) || (dx && !aligned16(dx)) || (x && !aligned16(x))) return KDCC_EALIGN;
-  if ((dw || dbias) && workspace_bytes < kdcc_dw_bwd_workspace_bytes(N, H, W, C, k, dil, pad, dtype))
+  if ((dw || dbias) && workspace_bytes < kdcc_dw_bwd_workspace_bytes(N, H, W, C, k, dil, pad, layout, dtype))
     return KDCC_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // transposed correlation = the forward loop over dy with mirrored taps and pad' = dil*(k-1) - pad
+  const int padt = dil * (k - 1) - pad;
+  if (layout == KDCC_LAYOUT_NCHW) {
+    if (dbias) return KDCC_ESHAPE;  // bias gradients go through kdcc_colsum on the NHWC path
+    if (dx) {
+      if (padt < 0) return KDCC_ESHAPE;
+      rc = dw_tc_conv(dy, w, nullptr, dx, N, C, Ho, Wo, H, W, k, dil, padt, 1, st);
+      if (rc) return rc;
+    }
+    if (dw) return dw_tc_wgrad(x, dy, dw, static_cast<float *>(workspace), N, C, H, W, Ho, Wo, k, dil, pad, st);
+    return KDCC_OK;
+  }
   const bool tma = use_tma(C, k, dil, dtype);
   if (dx) {
-    // transposed correlation = the forward loop over dy with mirrored taps and pad' = dil*(k-1) - pad
-    const int padt = dil * (k - 1) - pad;
     if (tma && padt >= 0) rc = dw_tma_conv(dy, w, nullptr, dx, N, Ho, Wo, C, H, W, k, dil, padt, 1, st);
     else if (dtype == KDCC_F32) rc = dw_direct_fwd<float>(dy, w, nullptr, dx, N, Ho, Wo, C, H, W, k, dil, padt, 1, st);
     else rc = dw_direct_fwd<__nv_bfloat16>(dy, w, nullptr, dx, N, Ho, Wo, C, H, W, k, dil, padt, 1, st);

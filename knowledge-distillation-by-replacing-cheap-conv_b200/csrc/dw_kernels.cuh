@@ -26,4 +26,12 @@ int dw_tma_wgrad_splits(int N, int Ho, int Wo, int C, int k, int dil);
 int dw_tma_wgrad(const void *x, const void *dy, float *dw, float *part, int N, int H, int W, int C, int Ho, int Wo,
                  int k, int dil, int pad, cudaStream_t st);
 
+// ---- tensor-core (tcgen05) bf16 kernels on NCHW planes: dw_tc.cu, dw_tc_wgrad.cu ---------------------
+bool dw_tc_supported(int Hi, int Wi, int Ho, int Wo, int k, int dil);
+int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int N, int C, int Hi, int Wi, int Ho,
+               int Wo, int k, int dil, int pad, int flip, cudaStream_t st);
+int dw_tc_wgrad(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, int Ho, int Wo,
+                int k, int dil, int pad, cudaStream_t st);
+size_t dw_tc_wgrad_workspace(int N, int C, int Ho, int Wo, int k);
+
 }  // namespace kdcc

@@ -1,0 +1,308 @@
+// Depthwise k x k convolution ON THE TENSOR CORES (tcgen05 + TMEM + TMA), bf16, NCHW planes.
+//
+// Why: a 9x9 depthwise tap set is 81 MAC per output element -- 20 MAC per HBM byte -- which is far past
+// the CUDA-core FFMA ridge of a B200 (dw_tma.cu measures ~14 TFMA/s, FFMA-issue-bound at ~10 % of HBM
+// speed).  Per channel the convolution along a row is a banded (Toeplitz) matrix product, so it can be
+// fed to tcgen05.mma; even at ~12 % structural efficiency the tensor pipe outruns the FFMA pipe by an
+// order of magnitude and the kernel becomes HBM/L2-bound again, as the north star asks.
+//
+// Formulation for one channel plane and a 128 x 128 output tile (i rows, j cols), dilation d, taps k:
+//     out[i][j] = sum_u  sum_{j'}  X[i + u*d][j'] * T_u[j'][j],      T_u[j'][j] = w[u][(j'-j)/d] (banded)
+//   = sum_u  A_u (128 x K) * B_u (K x 16)   per 16-column output slice, K = 16 + d(k-1) rounded to 16.
+//  * A_u is the SAME shared-memory tile for every u: TMA lands the (128+halo)-row input window once
+//    (128B-swizzled rows of 64 columns, out-of-bounds = zero = the conv padding); the tap-row shift u*d is
+//    a +128*u*d byte bump of the UMMA descriptor start address, the column slice of an output N-tile a
+//    +32 byte bump.  No im2col, no data movement.  (TMA needs a 16-byte aligned column origin, so the window
+//    starts up to 7 columns left of j0 - pad and the Toeplitz band is shifted right by the same amount.)
+//    KDCC_DW_TC_SINGLE=0 selects the conservative variant that lands one aligned 128-row tile per tap row.
+//  * B_u (16 x 64 bf16, 2 KB) is the Toeplitz band of one tap row; the band positions are identical for
+//    every channel, so the buffers are zeroed once and only the k*16*k band values are rewritten per plane.
+//  * D (128 x 128 fp32) lives in TMEM, double buffered: the epilogue of plane n overlaps the MMAs of n+1.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 build B for the NEXT plane then drain TMEM
+// for the current one (tcgen05.ld -> bf16 -> global).
+// The input-gradient form is the same kernel over dy with mirrored taps (flip) and pad' = d(k-1) - pad.
+// Reference semantics: models/students/transform_blocks/depthwise_separable_conv.py:7-8,12 (+ autograd).
+#include <stdlib.h>
+
+#include "dw_kernels.cuh"
+#include "sm100_ptx.cuh"
+
+namespace kdcc {
+
+constexpr int TC_TILE = 128;     // output rows and columns per tile (UMMA M = 128)
+constexpr int TC_THREADS = 192;
+
+struct DwTcParams {
+  int N, C, Hi, Wi, Ho, Wo, k, dil, pad, flip;
+  int halo;       // dil * (k - 1)
+  int nbox;       // 64-column boxes per A tile
+  int a_stages;   // A tiles in flight
+  int single;     // 1: one (128+halo)-row window per item, tap rows are descriptor row shifts; 0: one tile per tap row
+  int rows;       // rows per A tile: 128 (+ halo when single)
+  int box_bytes;  // ceil8(rows) * 128
+  int extra;      // zero columns added on the left so that the TMA column origin is 16-byte aligned
+  int ksteps;     // ceil((NT + halo) / 16)
+  int tiles_h, tiles_w;
+  long items;
+  const float *w, *bias;
+  __nv_bfloat16 *out;
+  int dbg;  // KDCC_TC_DEBUG: descriptor base-offset mode for row-shifted starts (0 none, 1 phase, 2 negated phase)
+};
+
+// K-major, SWIZZLE_128B operand tile: 128-byte rows, 8-row groups 1024 B apart, tile base 1024-byte aligned;
+// the start address may advance by 32-byte K slices inside the swizzle row.
+__device__ __forceinline__ uint64_t tc_desc(uint32_t addr, int base_mode = 1) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // SBO
+  d |= (uint64_t)1 << 46;                    // descriptor version
+  // The start may sit on any 128-byte row of the tile: the hardware derives the swizzle phase from the
+  // address bits, so the base-offset field stays 0 (measured on B200; setting it to the row phase breaks
+  // the results).  Modes 1/2 exist only to reproduce that measurement.
+  if (base_mode == 1) d |= (uint64_t)((addr >> 7) & 7) << 49;
+  else if (base_mode == 2) d |= (uint64_t)((8 - ((addr >> 7) & 7)) & 7) << 49;
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int a_stage_bytes = p.nbox * p.box_bytes;
+  constexpr int BU_BYTES = NT * 128;                 // one tap row's Toeplitz tile
+  const int b_stage_bytes = p.k * BU_BYTES;
+  const int AS = p.a_stages;
+  const uint32_t b_base = smem_base + AS * a_stage_bytes;
+  const uint32_t bar_base = b_base + 2 * b_stage_bytes;
+  auto b_full = [&](int s) { return bar_base + 8u * s; };
+  auto t_full = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto t_empty = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto a_full = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto a_empty = [&](int s) { return bar_base + 8u * (6 + 8 + s); };  // up to 8 A stages
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_gen + (bar_base - smem_base) + 8 * 22);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(b_full(s), 128);
+      ptx::mbar_init(t_full(s), 1);
+      ptx::mbar_init(t_empty(s), 4);
+    }
+    for (int s = 0; s < AS; ++s) {
+      ptx::mbar_init(a_full(s), 1);
+      ptx::mbar_init(a_empty(s), 1);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tm_in);
+  }
+  if (warp == 1) ptx::tmem_alloc<2 * TC_TILE>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)));
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](long item, int &n, int &c, int &i0, int &j0) {
+    const int tj = (int)(item % p.tiles_w); item /= p.tiles_w;
+    const int ti = (int)(item % p.tiles_h); item /= p.tiles_h;
+    c = (int)(item % p.C);
+    n = (int)(item / p.C);
+    i0 = ti * TC_TILE;
+    j0 = tj * TC_TILE;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: the input window of an item, once (single) or once per tap row =====
+    int as = 0; uint32_t aph = 0;
+    const int tiles = p.single ? 1 : p.k;
+    for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, c, i0, j0;
+      decode(item, n, c, i0, j0);
+      for (int u = 0; u < tiles; ++u) {
+        ptx::mbar_wait(a_empty(as), aph ^ 1);
+        ptx::mbar_arrive_expect_tx(a_full(as), (uint32_t)(p.nbox * p.rows * 128));
+        for (int b = 0; b < p.nbox; ++b)
+          ptx::tma_load_4d(smem_base + as * a_stage_bytes + b * p.box_bytes, &tm_in, a_full(as),
+                           j0 - p.pad - p.extra + 64 * b, i0 - p.pad + u * p.dil, c, n);
+        if (++as == AS) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    // instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, N = NT, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+    int it = 0;
+    int as = 0; uint32_t aph = 0;
+    for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      ptx::mbar_wait(t_empty(s), ph ^ 1);
+      ptx::mbar_wait(b_full(s), ph);
+      const uint32_t b0 = b_base + s * b_stage_bytes;
+      const uint32_t d0 = tmem_base + (uint32_t)(s * TC_TILE);
+      for (int u = 0; u < p.k; ++u) {
+        if (!p.single || u == 0) ptx::mbar_wait(a_full(as), aph);
+        ptx::tcgen05_fence_after();
+        // single window: tap row u starts u*dil rows further down the same tile
+        const uint32_t a0 = smem_base + as * a_stage_bytes + (p.single ? (uint32_t)(u * p.dil) * 128u : 0u);
+        const uint32_t b_u = b0 + (uint32_t)u * BU_BYTES;
+#pragma unroll 1
+        for (int t = 0; t < TC_TILE / NT; ++t) {
+          for (int kk = 0; kk < p.ksteps; ++kk) {
+            const int q0 = t * NT + kk * 16;  // first window column of this 16-wide reduction slice
+            const uint32_t a_addr = a0 + (uint32_t)(q0 >> 6) * (uint32_t)p.box_bytes + (uint32_t)(q0 & 63) * 2u;
+            ptx::umma_f16(d0 + (uint32_t)(t * NT), tc_desc(a_addr, p.dbg), tc_desc(b_u + kk * 32), idesc, (u | kk) ? 1u : 0u);
+          }
+        }
+        if (!p.single || u == p.k - 1) {
+          ptx::umma_commit(a_empty(as));  // tile free once these MMAs have read it
+          if (++as == AS) { as = 0; aph ^= 1; }
+        }
+      }
+      ptx::umma_commit(t_full(s));
+    }
+  } else if (warp >= 2) {
+    // ===== Toeplitz builder + epilogue (128 threads) =====
+    const int et = threadIdx.x - 64;  // 0..127
+    const int quad = warp & 3;
+    // zero both B stages once: the band positions never change, only their values
+    for (int i = et; i < 2 * b_stage_bytes / 16; i += 128)
+      *reinterpret_cast<uint4 *>(smem_gen + (b_base - smem_base) + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
+    auto build_b = [&](long item, int s) {
+      int n, c, i0, j0;
+      decode(item, n, c, i0, j0);
+      const float *wc = p.w + (long)c * p.k * p.k;
+      uint8_t *bs = smem_gen + (b_base - smem_base) + (size_t)s * b_stage_bytes;
+      const int band = p.k * NT * p.k;
+      for (int e = et; e < band; e += 128) {
+        const int v = e % p.k;
+        const int j = (e / p.k) % NT;
+        const int u = e / (p.k * NT);
+        const int jp = j + v * p.dil + p.extra;  // reduction column that feeds output column j through tap v
+        const float wv = __ldg(wc + (p.flip ? (p.k - 1 - u) * p.k + (p.k - 1 - v) : u * p.k + v));
+        const int off = u * BU_BYTES + (j >> 3) * 1024 + (j & 7) * 128 + ((((jp >> 3) ^ (j & 7)) & 7) << 4) + (jp & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(bs + off) = __float2bfloat16_rn(wv);
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(b_full(s));
+    };
+
+    if ((long)blockIdx.x < p.items) build_b(blockIdx.x, 0);
+    int it = 0;
+    for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const long next = item + gridDim.x;
+      // stage s^1 was last read by the MMAs of item it-1, whose completion we observed through t_full
+      if (next < p.items) build_b(next, s ^ 1);
+      int n, c, i0, j0;
+      decode(item, n, c, i0, j0);
+      ptx::mbar_wait(t_full(s), ph);
+      ptx::tcgen05_fence_after();
+      const int gi = i0 + quad * 32 + lane;
+      const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
+      __nv_bfloat16 *orow = p.out + (((long)n * p.C + c) * p.Ho + gi) * p.Wo + j0;
+      const uint32_t t_row = tmem_base + (uint32_t)(s * TC_TILE) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < TC_TILE / 32; ++ch) {
+        uint32_t vr[32];
+        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, vr);
+        ptx::tmem_ld_wait();
+        if (gi < p.Ho) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = j0 + ch * 32 + q * 8;
+            if (col < p.Wo) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(vr[8 * q + 0]) + bias, __uint_as_float(vr[8 * q + 1]) + bias);
+              o.y = pack_bf16x2(__uint_as_float(vr[8 * q + 2]) + bias, __uint_as_float(vr[8 * q + 3]) + bias);
+              o.z = pack_bf16x2(__uint_as_float(vr[8 * q + 4]) + bias, __uint_as_float(vr[8 * q + 5]) + bias);
+              o.w = pack_bf16x2(__uint_as_float(vr[8 * q + 6]) + bias, __uint_as_float(vr[8 * q + 7]) + bias);
+              *reinterpret_cast<uint4 *>(orow + ch * 32 + q * 8) = o;
+            }
+          }
+        }
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(t_empty(s));
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<2 * TC_TILE>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int tc_extra(int pad) { return (8 - pad % 8) % 8; }
+static int tc_nt(int reach) { return reach + 32 <= 64 ? 32 : 16; }  // reach = halo + alignment columns
+
+bool dw_tc_supported(int Hi, int Wi, int Ho, int Wo, int k, int dil) {
+  (void)Hi; (void)Ho;
+  const int halo = dil * (k - 1);
+  if (k > 9 || k % 2 == 0) return false;      // wgrad keeps k*k register partials: instantiated for k = 1,3,5,7,9
+  if (halo + 7 + 16 > 64) return false;       // one 64-column swizzle group per Toeplitz tile (incl. alignment columns)
+  if (Wi % 8 != 0 || Wo % 8 != 0) return false;  // 16-byte rows for TMA strides and epilogue stores
+  return true;
+}
+
+template <int NT>
+static int tc_conv_launch(const void *in, const DwTcParams &p0, cudaStream_t st) {
+  DwTcParams p = p0;
+  p.ksteps = ceil_div(NT + p.halo + p.extra, 16);
+  p.nbox = ceil_div((TC_TILE - NT) + p.ksteps * 16, 64);  // the last N-tile's last reduction slice ends here
+  p.rows = TC_TILE + (p.single ? p.halo : 0);
+  p.box_bytes = (p.rows + 7) / 8 * 8 * 128;
+  const int b_bytes = 2 * p.k * NT * 128;
+  p.a_stages = min(p.single ? 2 : 8, (int)((220 * 1024 - b_bytes - 1024) / (p.nbox * p.box_bytes)));
+  if (p.a_stages < 2) return KDCC_ESHAPE;
+  CUtensorMap tm;
+  const uint64_t dims[4] = {(uint64_t)p.Wi, (uint64_t)p.Hi, (uint64_t)p.C, (uint64_t)p.N};
+  const uint64_t strides[3] = {(uint64_t)p.Wi * 2, (uint64_t)p.Hi * p.Wi * 2, (uint64_t)p.C * p.Hi * p.Wi * 2};
+  const uint32_t box[4] = {64, (uint32_t)p.rows, 1, 1};
+  int rc = make_tmap_bf16(&tm, in, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const int smem = p.a_stages * p.nbox * p.box_bytes + b_bytes + 256 + 1024;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(dw_tc_conv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_smem = smem;
+  }
+  const int grid = (int)min(p.items, (long)kNumSMs);
+  dw_tc_conv_kernel<NT><<<grid, TC_THREADS, smem, st>>>(tm, p);
+  return launch_status();
+}
+
+int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int N, int C, int Hi, int Wi, int Ho,
+               int Wo, int k, int dil, int pad, int flip, cudaStream_t st) {
+  DwTcParams p{};
+  p.N = N; p.C = C; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo; p.k = k; p.dil = dil; p.pad = pad; p.flip = flip;
+  p.halo = dil * (k - 1);
+  p.tiles_h = ceil_div(Ho, TC_TILE);
+  p.tiles_w = ceil_div(Wo, TC_TILE);
+  p.items = (long)N * C * p.tiles_h * p.tiles_w;
+  p.w = w; p.bias = bias;
+  p.out = static_cast<__nv_bfloat16 *>(out);
+  if (p.items == 0) return KDCC_OK;
+  const char *dbg = getenv("KDCC_TC_DEBUG");
+  p.dbg = dbg ? atoi(dbg) : 0;
+  p.extra = tc_extra(pad);
+  const char *sg = getenv("KDCC_DW_TC_SINGLE");
+  p.single = sg ? atoi(sg) : 1;
+  if (TC_TILE + p.halo > 256) p.single = 0;  // TMA box rows
+  const char *e = getenv("KDCC_DW_TC_NT");
+  const int nt = e ? atoi(e) : tc_nt(p.halo + p.extra);
+  if (nt == 32 && p.halo + p.extra + 32 <= 64) return tc_conv_launch<32>(in, p, st);
+  return tc_conv_launch<16>(in, p, st);
+}
+
+}  // namespace kdcc

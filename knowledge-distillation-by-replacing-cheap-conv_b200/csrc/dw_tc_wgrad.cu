@@ -1,0 +1,322 @@
+// Depthwise weight gradient ON THE TENSOR CORES (tcgen05 + TMEM + TMA), bf16, NCHW planes.
+//
+//   dw[c][u][v] = sum_{n,i,j} dy[n][c][i][j] * x[n][c][i + u*d - p][j + v*d - p]
+//
+// For one channel plane and one 128 x 128 dy tile, with xw the (128+halo)^2 input window whose origin is
+// (i0 - p, j0 - p) and zero outside the image:
+//     P_u[j][q] = sum_i dy[i][j] * xw[i + u*d][q]           (a 128 x (128+halo) matrix, reduction over rows)
+//     dw[u][v] += sum_j P_u[j][j + v*d]                      (k diagonals of P_u)
+// P_u is one tcgen05.mma chain per tap row u: A = dy^T and B = xw[u*d ...] are both "MN-major" views of
+// 128B-swizzled tiles TMA landed (no transposes); the tap-row shift u*d is a +128*u*d byte bump of the
+// B descriptor start address into the one (128+halo)-row window TMA landed for the plane.
+// (KDCC_DW_TC_SINGLE=0: conservative variant, one aligned 128-row x tile per tap row.)
+// Only k of the 128+halo columns of each P_u row are needed, so the FFMA-bound CUDA-core formulation
+// (dw_tma.cu: ~14 TFMA/s) is replaced by ~5 % efficient but 50x faster tensor-core work.
+// The epilogue warps pull P_u out of TMEM 32 columns at a time, pick the k diagonal entries of their row
+// through a private shared-memory scratch row (dynamic column index), and keep the k*k partial sums in
+// registers across all planes of the channel; a warp-shuffle + fixed-order cross-warp sum finishes the
+// channel.  Deterministic: no atomics, splits (if any) are reduced by dw_wgrad_reduce_kernel.
+// Reference semantics: autograd of models/students/transform_blocks/depthwise_separable_conv.py:12.
+#include <stdlib.h>
+
+#include "dw_kernels.cuh"
+#include "sm100_ptx.cuh"
+
+namespace kdcc {
+
+constexpr int WG_TILE = 128;
+constexpr int WG_THREADS = 192;
+constexpr int WG_SCR_PITCH = 36;  // floats per scratch row: 16-byte aligned rows, conflict-free 128-bit stores
+
+struct DwTcWgradParams {
+  int N, C, H, W, Ho, Wo, k, dil, pad;
+  int halo, nbox, x_stages;         // 64-column boxes per x tile, x tiles in flight
+  int single, rows, box_bytes;      // single: one (128+halo)-row window per plane; rows per box; bytes per box
+  int extra;                        // zero columns on the left so that the TMA column origin is 16-byte aligned
+  int nq;                           // P_u columns: (128 + halo) rounded up to 16
+  int tiles_h, tiles_w, planes;     // planes = N * tiles_h * tiles_w (per channel)
+  int splits;                       // CTAs sharing one channel
+  long pairs;                       // C * splits
+  float *out;                       // [splits][C][k*k] (or dw itself when splits == 1)
+};
+
+// MN-major SWIZZLE_128B operand: 64-element groups `lbo` bytes apart, 8-row (reduction) groups 1024 B apart
+__device__ __forceinline__ uint64_t wg_desc(uint32_t addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+constexpr int WG_BOX = WG_TILE * 128;  // 128 rows x 64 columns, swizzled
+
+template <int K>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
+                   const DwTcWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int x_bytes = p.nbox * p.box_bytes;
+  const int XS = p.x_stages;
+  const uint32_t dy_base = smem_base + XS * x_bytes;
+  const uint32_t scr_off = XS * x_bytes + 4 * WG_BOX;
+  const uint32_t bar_base = smem_base + scr_off + 4 * 32 * WG_SCR_PITCH * 4;
+  auto dy_full = [&](int s) { return bar_base + 8u * s; };
+  auto dy_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto t_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto t_empty = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto x_full = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto x_empty = [&](int s) { return bar_base + 8u * (12 + s); };  // up to 4 x stages
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_gen + (bar_base - smem_base) + 128);
+  float *red = reinterpret_cast<float *>(smem_gen + (bar_base - smem_base) + 192);  // [4][K*K]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(dy_full(s), 1);
+      ptx::mbar_init(dy_empty(s), 1);
+      ptx::mbar_init(t_full(s), 1);
+      ptx::mbar_init(t_empty(s), 4);
+    }
+    for (int s = 0; s < XS; ++s) {
+      ptx::mbar_init(x_full(s), 1);
+      ptx::mbar_init(x_empty(s), 1);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tm_x);
+    ptx::prefetch_tensormap(&tm_dy);
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)));
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode_plane = [&](int pl, int &n, int &i0, int &j0) {
+    const int tj = pl % p.tiles_w; pl /= p.tiles_w;
+    const int ti = pl % p.tiles_h;
+    n = pl / p.tiles_h;
+    i0 = ti * WG_TILE;
+    j0 = tj * WG_TILE;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer: dy tile once per plane, one x tile per tap row =====
+    int it = 0;
+    int xs = 0; uint32_t xph = 0;
+    for (long pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+      const int c = (int)(pair % p.C), split = (int)(pair / p.C);
+      for (int pl = split; pl < p.planes; pl += p.splits, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        int n, i0, j0;
+        decode_plane(pl, n, i0, j0);
+        ptx::mbar_wait(dy_empty(s), ph ^ 1);
+        ptx::mbar_arrive_expect_tx(dy_full(s), 2 * WG_BOX);
+        for (int b = 0; b < 2; ++b)
+          ptx::tma_load_4d(dy_base + (2 * s + b) * WG_BOX, &tm_dy, dy_full(s), j0 + 64 * b, i0, c, n);
+        for (int u = 0; u < (p.single ? 1 : K); ++u) {
+          ptx::mbar_wait(x_empty(xs), xph ^ 1);
+          ptx::mbar_arrive_expect_tx(x_full(xs), (uint32_t)(p.nbox * p.rows * 128));
+          for (int b = 0; b < p.nbox; ++b)
+            ptx::tma_load_4d(smem_base + xs * x_bytes + b * p.box_bytes, &tm_x, x_full(xs),
+                             j0 - p.pad - p.extra + 64 * b, i0 - p.pad + u * p.dil, c, n);
+          if (++xs == XS) { xs = 0; xph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer: P_u = dy^T (128 cols x 128 rows) * x_u (128 rows x nq cols) =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(p.nq >> 3) << 17) | ((uint32_t)(WG_TILE >> 4) << 24);
+    int it = 0, tit = 0;
+    int xs = 0; uint32_t xph = 0;
+    for (long pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+      const int split = (int)(pair / p.C);
+      for (int pl = split; pl < p.planes; pl += p.splits, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        ptx::mbar_wait(dy_full(s), ph);
+        const uint32_t dys = dy_base + 2 * s * WG_BOX;
+        for (int u = 0; u < K; ++u, ++tit) {
+          const int tb = tit & 1;
+          if (!p.single || u == 0) ptx::mbar_wait(x_full(xs), xph);
+          ptx::mbar_wait(t_empty(tb), ((tit >> 1) & 1) ^ 1);
+          ptx::tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(tb * 256);
+          // single window: tap row u starts u*dil rows (128 B each) further down the same tile
+          const uint32_t xa = smem_base + xs * x_bytes + (p.single ? (uint32_t)(u * p.dil) * 128u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < WG_TILE / 16; ++ks)  // 16 reduction rows per MMA = 2 KB in both tiles
+            ptx::umma_f16(d_tmem, wg_desc(dys + ks * 2048, WG_BOX), wg_desc(xa + ks * 2048, (uint32_t)p.box_bytes), idesc,
+                          ks ? 1u : 0u);
+          ptx::umma_commit(t_full(tb));
+          if (!p.single || u == K - 1) {
+            ptx::umma_commit(x_empty(xs));
+            if (++xs == XS) { xs = 0; xph ^= 1; }
+          }
+        }
+        ptx::umma_commit(dy_empty(s));
+      }
+    }
+  } else if (warp >= 2) {
+    // ===== epilogue: diagonals of P_u -> k*k register partial sums =====
+    const int quad = warp & 3;
+    float *scr = reinterpret_cast<float *>(smem_gen + scr_off) + (quad * 32 + lane) * WG_SCR_PITCH;
+    const int nch = (31 + p.halo + p.extra) / 32 + 1;  // 32-column chunks a warp's rows reach into
+    int tit = 0;
+    for (long pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+      const int c = (int)(pair % p.C), split = (int)(pair / p.C);
+      float acc[K][K];
+#pragma unroll
+      for (int u = 0; u < K; ++u)
+#pragma unroll
+        for (int v = 0; v < K; ++v) acc[u][v] = 0.f;
+      for (int pl = split; pl < p.planes; pl += p.splits) {
+#pragma unroll
+        for (int u = 0; u < K; ++u, ++tit) {
+          const int tb = tit & 1;
+          ptx::mbar_wait(t_full(tb), (tit >> 1) & 1);
+          ptx::tcgen05_fence_after();
+          const uint32_t t_row = tmem_base + (uint32_t)(tb * 256) + ((uint32_t)(quad * 32) << 16);
+          for (int c3 = 0; c3 < nch; ++c3) {
+            const int col0 = 32 * (quad + c3);
+            if (col0 >= p.nq) break;
+            uint32_t vr[32];
+            ptx::tmem_ld_32x32b_x32(t_row + col0, vr);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4 *>(scr + 4 * q) = make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
+#pragma unroll
+            for (int v = 0; v < K; ++v) {
+              const int e = lane + v * p.dil + p.extra - 32 * c3;  // window column of tap v for row j, relative to this chunk
+              if (e >= 0 && e < 32) acc[u][v] += scr[e];
+            }
+          }
+          ptx::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(t_empty(tb));
+        }
+      }
+      // channel (pair) finished: sum the 128 rows -- shuffle inside the warp, fixed order across warps
+#pragma unroll
+      for (int u = 0; u < K; ++u)
+#pragma unroll
+        for (int v = 0; v < K; ++v) {
+          const float r = warp_sum(acc[u][v]);
+          if (lane == 0) red[quad * K * K + u * K + v] = r;
+        }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 64;
+      if (et < K * K) {
+        // warps 2,3,4,5 own quadrants 2,3,0,1: add in quadrant order 0..3 for a fixed summation order
+        const float sum = ((red[0 * K * K + et] + red[1 * K * K + et]) + red[2 * K * K + et]) + red[3 * K * K + et];
+        p.out[((long)split * p.C + c) * (K * K) + et] = sum;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// dw[c][tap] = sum_s part[s][c][tap]
+__global__ void dw_tc_wgrad_reduce_kernel(const float *__restrict__ part, float *__restrict__ dw, int splits, long count) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += part[(long)s * count + i];
+  dw[i] = acc;
+}
+
+static int wg_splits(int C, int planes) {
+  int best = 1;
+  long best_cost = -1;
+  for (int s = 1; s <= planes && s <= 16; ++s) {
+    const long rounds = ceil_div<long>((long)C * s, kNumSMs);
+    const long cost = rounds * ceil_div(planes, s) * 16 + rounds;  // planes per CTA dominate; small per-pair overhead
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+size_t dw_tc_wgrad_workspace(int N, int C, int Ho, int Wo, int k) {
+  const int planes = N * ceil_div(Ho, WG_TILE) * ceil_div(Wo, WG_TILE);
+  return (size_t)wg_splits(C, planes) * C * k * k * sizeof(float) + 16;
+}
+
+template <int K>
+static int wgrad_launch(const void *x, const void *dy, float *dw, float *part, const DwTcWgradParams &p0, cudaStream_t st) {
+  DwTcWgradParams p = p0;
+  CUtensorMap tm_x, tm_dy;
+  {
+    const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.C, (uint64_t)p.N};
+    const uint64_t strides[3] = {(uint64_t)p.W * 2, (uint64_t)p.H * p.W * 2, (uint64_t)p.C * p.H * p.W * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.rows, 1, 1};
+    int rc = make_tmap_bf16(&tm_x, x, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.C, (uint64_t)p.N};
+    const uint64_t strides[3] = {(uint64_t)p.Wo * 2, (uint64_t)p.Ho * p.Wo * 2, (uint64_t)p.C * p.Ho * p.Wo * 2};
+    const uint32_t box[4] = {64, WG_TILE, 1, 1};
+    int rc = make_tmap_bf16(&tm_dy, dy, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  p.out = p.splits == 1 ? dw : part;
+  const int fixed = 4 * WG_BOX + 4 * 32 * WG_SCR_PITCH * 4 + 192 + 4 * K * K * 4 + 64 + 1024;
+  p.x_stages = min(p.single ? 2 : 4, (220 * 1024 - fixed) / (p.nbox * p.box_bytes));
+  if (p.x_stages < 2) return KDCC_ESHAPE;
+  const int smem = p.x_stages * p.nbox * p.box_bytes + fixed;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(dw_tc_wgrad_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_smem = smem;
+  }
+  const int grid = (int)min(p.pairs, (long)kNumSMs);
+  dw_tc_wgrad_kernel<K><<<grid, WG_THREADS, smem, st>>>(tm_x, tm_dy, p);
+  int rc = launch_status();
+  if (rc || p.splits == 1) return rc;
+  const long count = (long)p.C * K * K;
+  dw_tc_wgrad_reduce_kernel<<<(unsigned)ceil_div<long>(count, 256), 256, 0, st>>>(part, dw, p.splits, count);
+  return launch_status();
+}
+
+int dw_tc_wgrad(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, int Ho, int Wo,
+                int k, int dil, int pad, cudaStream_t st) {
+  DwTcWgradParams p{};
+  p.N = N; p.C = C; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.k = k; p.dil = dil; p.pad = pad;
+  p.halo = dil * (k - 1);
+  p.extra = (8 - pad % 8) % 8;
+  p.nq = (WG_TILE + p.halo + p.extra + 15) / 16 * 16;
+  p.nbox = ceil_div(p.nq, 64);
+  const char *sg = getenv("KDCC_DW_TC_SINGLE");
+  p.single = sg ? atoi(sg) : 1;
+  if (WG_TILE + p.halo > 256) p.single = 0;
+  p.rows = WG_TILE + (p.single ? p.halo : 0);
+  p.box_bytes = (p.rows + 7) / 8 * 8 * 128;
+  p.tiles_h = ceil_div(Ho, WG_TILE);
+  p.tiles_w = ceil_div(Wo, WG_TILE);
+  p.planes = N * p.tiles_h * p.tiles_w;
+  p.splits = wg_splits(C, p.planes);
+  p.pairs = (long)C * p.splits;
+  if (p.nq > 256) return KDCC_ESHAPE;
+  switch (k) {
+    case 1: return wgrad_launch<1>(x, dy, dw, part, p, st);
+    case 3: return wgrad_launch<3>(x, dy, dw, part, p, st);
+    case 5: return wgrad_launch<5>(x, dy, dw, part, p, st);
+    case 7: return wgrad_launch<7>(x, dy, dw, part, p, st);
+    case 9: return wgrad_launch<9>(x, dy, dw, part, p, st);
+    default: return KDCC_ESHAPE;
+  }
+}
+
+}  // namespace kdcc

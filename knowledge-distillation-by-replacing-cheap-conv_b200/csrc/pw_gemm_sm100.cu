@@ -27,10 +27,16 @@ constexpr int GEMM_BR = 64;    // reduction elements per stage = one 128-byte sw
 constexpr int GEMM_THREADS = 192;
 
 struct GemmParams {
-  int I, J, R;          // logical extents
+  int I, J, R;          // logical extents (R per batch entry)
+  int batch;            // independent GEMMs (NCHW images); 1 for the NHWC forms
+  int a_batched, b_batched;  // operand has a batch dimension (else it is shared, e.g. the weights)
+  int r_spans_batch;    // dW on NCHW: the reduction runs over (batch, r) and the output is not batched
+  long out_batch_stride;     // elements between batch entries of the output
+  int affine_rows;      // scale/shift indexed by output row i (NCHW: channel = row) instead of column j
   int tiles_i, tiles_j; // output tiling
   int splits;           // CTAs sharing one output tile along r (dW only)
-  int rblocks;          // ceil(R / 64)
+  int rblocks;          // reduction blocks of 64: ceil(R / 64) (* batch when r_spans_batch)
+  int rblocks_per_batch;
   // epilogue
   __nv_bfloat16 *out_raw, *out_act;  // [I][J] bf16, either may be null
   const float *scale, *shift;        // per j, may be null
@@ -102,7 +108,8 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long items = (long)p.tiles_i * p.tiles_j * p.splits;
+  const int out_batches = p.r_spans_batch ? 1 : p.batch;
+  const long items = (long)p.tiles_i * p.tiles_j * p.splits * out_batches;
   const int rb_per_split = (p.rblocks + p.splits - 1) / p.splits;
 
   if (warp == 0 && lane == 0) {
@@ -110,27 +117,33 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     int s = 0; uint32_t ph = 0;
     for (long item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = (int)(item % p.splits);
-      const long tile = item / p.splits;
-      const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+      long tile = item / p.splits;
+      const int tj = (int)(tile % p.tiles_j); tile /= p.tiles_j;
+      const int ti = (int)(tile % p.tiles_i);
+      const int bo = (int)(tile / p.tiles_i);  // output batch entry
       const int rb0 = split * rb_per_split, rb1 = min(p.rblocks, rb0 + rb_per_split);
       for (int rb = rb0; rb < rb1; ++rb) {
+        // reduction block -> (batch entry, block inside the entry)
+        const int bz = p.r_spans_batch ? rb / p.rblocks_per_batch : bo;
+        const int rl = p.r_spans_batch ? rb % p.rblocks_per_batch : rb;
+        const int za = p.a_batched ? bz : 0, zb = p.b_batched ? bz : 0;
         ptx::mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
         const uint32_t b_dst = a_dst + Cfg::A_BYTES;
         ptx::mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
         if (!A_MN) {
-          ptx::tma_load_2d(a_dst, &tm_a, full_bar(s), rb * GEMM_BR, ti * GEMM_BI);
+          ptx::tma_load_3d(a_dst, &tm_a, full_bar(s), rl * GEMM_BR, ti * GEMM_BI, za);
         } else {
 #pragma unroll
           for (int b = 0; b < GEMM_BI / 64; ++b)
-            ptx::tma_load_2d(a_dst + b * 8192, &tm_a, full_bar(s), ti * GEMM_BI + b * 64, rb * GEMM_BR);
+            ptx::tma_load_3d(a_dst + b * 8192, &tm_a, full_bar(s), ti * GEMM_BI + b * 64, rl * GEMM_BR, za);
         }
         if (!B_MN) {
-          ptx::tma_load_2d(b_dst, &tm_b, full_bar(s), rb * GEMM_BR, tj * BJ);
+          ptx::tma_load_3d(b_dst, &tm_b, full_bar(s), rl * GEMM_BR, tj * BJ, zb);
         } else {
 #pragma unroll
           for (int b = 0; b < BJ / 64; ++b)
-            ptx::tma_load_2d(b_dst + b * 8192, &tm_b, full_bar(s), tj * BJ + b * 64, rb * GEMM_BR);
+            ptx::tma_load_3d(b_dst + b * 8192, &tm_b, full_bar(s), tj * BJ + b * 64, rl * GEMM_BR, zb);
         }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -170,8 +183,10 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     int as = 0; uint32_t aph = 0;
     for (long item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = (int)(item % p.splits);
-      const long tile = item / p.splits;
-      const int tj = (int)(tile % p.tiles_j), ti = (int)(tile / p.tiles_j);
+      long tile = item / p.splits;
+      const int tj = (int)(tile % p.tiles_j); tile /= p.tiles_j;
+      const int ti = (int)(tile % p.tiles_i);
+      const long obase = (long)(tile / p.tiles_i) * p.out_batch_stride;
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tcgen05_fence_after();
       const int row = ti * GEMM_BI + quad * 32 + lane;
@@ -191,7 +206,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                 *reinterpret_cast<uint4 *>(dst + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           } else {
             if (p.out_raw != nullptr) {
-              __nv_bfloat16 *dst = p.out_raw + (long)row * p.J + col0;
+              __nv_bfloat16 *dst = p.out_raw + obase + (long)row * p.J + col0;
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 if (col0 + q * 8 < p.J) {
@@ -204,17 +219,17 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                 }
             }
             if (p.out_act != nullptr) {
-              __nv_bfloat16 *dst = p.out_act + (long)row * p.J + col0;
+              __nv_bfloat16 *dst = p.out_act + obase + (long)row * p.J + col0;
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 if (col0 + q * 8 < p.J) {
                   float f[8];
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
-                    const int col = col0 + q * 8 + e;
+                    const int ch = p.affine_rows ? row : col0 + q * 8 + e;
                     float x = __uint_as_float(v[8 * q + e]);
-                    if (p.scale) x *= __ldg(p.scale + col);
-                    if (p.shift) x += __ldg(p.shift + col);
+                    if (p.scale) x *= __ldg(p.scale + ch);
+                    if (p.shift) x += __ldg(p.shift + ch);
                     if (p.relu) x = fmaxf(x, 0.f);
                     f[e] = x;
                   }
@@ -254,12 +269,13 @@ __global__ void reduce_splits_kernel(const float *__restrict__ part, float *__re
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-// 2-D bf16 map, 128B swizzle: inner extent `inner` (contiguous), outer extent `outer`, box (64, box_outer)
-static int gemm_map(CUtensorMap *m, const void *base, long inner, long outer, int box_outer) {
-  const uint64_t dims[2] = {(uint64_t)inner, (uint64_t)outer};
-  const uint64_t strides[1] = {(uint64_t)inner * 2};
-  const uint32_t box[2] = {64, (uint32_t)box_outer};
-  return make_tmap_bf16(m, base, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+// 3-D bf16 map, 128B swizzle: inner extent `inner` (contiguous), outer extent `outer`, `batch` entries of
+// inner*outer elements; box (64, box_outer, 1)
+static int gemm_map(CUtensorMap *m, const void *base, long inner, long outer, int batch, int box_outer) {
+  const uint64_t dims[3] = {(uint64_t)inner, (uint64_t)outer, (uint64_t)batch};
+  const uint64_t strides[2] = {(uint64_t)inner * 2, (uint64_t)inner * (uint64_t)outer * 2};
+  const uint32_t box[3] = {64, (uint32_t)box_outer, 1};
+  return make_tmap_bf16(m, base, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 template <int BJ, bool A_MN, bool B_MN>
@@ -268,11 +284,14 @@ static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaS
   GemmParams p = p0;
   p.tiles_i = ceil_div(p.I, GEMM_BI);
   p.tiles_j = ceil_div(p.J, BJ);
-  p.rblocks = ceil_div(p.R, GEMM_BR);
+  if (p.batch < 1) p.batch = 1;
+  p.rblocks_per_batch = ceil_div(p.R, GEMM_BR);
+  p.rblocks = p.rblocks_per_batch * (p.r_spans_batch ? p.batch : 1);
   CUtensorMap tm_a, tm_b;
-  int rc = A_MN ? gemm_map(&tm_a, a, p.I, p.R, 64) : gemm_map(&tm_a, a, p.R, p.I, GEMM_BI);
+  const int ba = p.a_batched ? p.batch : 1, bb = p.b_batched ? p.batch : 1;
+  int rc = A_MN ? gemm_map(&tm_a, a, p.I, p.R, ba, 64) : gemm_map(&tm_a, a, p.R, p.I, ba, GEMM_BI);
   if (rc) return rc;
-  rc = B_MN ? gemm_map(&tm_b, b, p.J, p.R, 64) : gemm_map(&tm_b, b, p.R, p.J, BJ);
+  rc = B_MN ? gemm_map(&tm_b, b, p.J, p.R, bb, 64) : gemm_map(&tm_b, b, p.R, p.J, bb, BJ);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -281,7 +300,7 @@ static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaS
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const long items = (long)p.tiles_i * p.tiles_j * p.splits;
+  const long items = (long)p.tiles_i * p.tiles_j * p.splits * (p.r_spans_batch ? 1 : p.batch);
   const int grid = (int)min(items, (long)kNumSMs);
   pw_gemm_sm100_kernel<BJ, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(tm_a, tm_b, p);
   return launch_status();
@@ -294,45 +313,81 @@ static int gemm_dispatch_bj(const void *a, const void *b, const GemmParams &p, c
   return gemm_launch<64, A_MN, B_MN>(a, b, p, st);
 }
 
-bool pw_sm100_supported(long M, int K, int Nc) {
+bool pw_sm100_supported(long M, int K, int Nc, int batch, int layout) {
   // 16-byte global strides for TMA and 16-byte epilogue stores
-  return M > 0 && K % 8 == 0 && Nc % 8 == 0 && M < (1L << 31);
+  if (M <= 0 || M >= (1L << 31) || K % 8 != 0) return false;
+  if (layout == KDCC_LAYOUT_NCHW) return batch > 0 && M % batch == 0 && (M / batch) % 8 == 0;
+  return Nc % 8 == 0;
 }
 
 int pw_sm100_fwd(const void *x, const void *w, const float *scale, const float *shift, int relu, void *y_raw,
-                 void *y_act, long M, int K, int Nc, cudaStream_t st) {
+                 void *y_act, long M, int K, int Nc, int batch, int layout, cudaStream_t st) {
   GemmParams p{};
-  p.I = (int)M; p.J = Nc; p.R = K; p.splits = 1;
   p.out_raw = static_cast<__nv_bfloat16 *>(y_raw);
   p.out_act = static_cast<__nv_bfloat16 *>(y_act);
-  p.scale = scale; p.shift = shift; p.relu = relu;
-  return gemm_dispatch_bj<false, false>(x, w, p, st);
+  p.scale = scale; p.shift = shift; p.relu = relu; p.splits = 1;
+  if (layout == KDCC_LAYOUT_NHWC) {
+    // y[m][n] = sum_k x[m][k] w[n][k]
+    p.I = (int)M; p.J = Nc; p.R = K; p.batch = 1;
+    return gemm_dispatch_bj<false, false>(x, w, p, st);
+  }
+  // NCHW: y_b[n][pix] = sum_k w[n][k] x_b[k][pix] : A = w (shared, K-major), B = x_b (pixel-contiguous, MN-major)
+  const int P = (int)(M / batch);
+  p.I = Nc; p.J = P; p.R = K; p.batch = batch; p.a_batched = 0; p.b_batched = 1;
+  p.out_batch_stride = (long)Nc * P; p.affine_rows = 1;
+  return gemm_dispatch_bj<false, true>(w, x, p, st);
 }
 
-int pw_sm100_bwd_dx(const void *dy, const void *w, void *dx, long M, int K, int Nc, cudaStream_t st) {
-  // dx[m][k] = sum_n dy[m][n] w[n][k] : j = k, r = n; W [Nc][K] is j-contiguous -> MN-major B
+int pw_sm100_bwd_dx(const void *dy, const void *w, void *dx, long M, int K, int Nc, int batch, int layout, cudaStream_t st) {
   GemmParams p{};
-  p.I = (int)M; p.J = K; p.R = Nc; p.splits = 1;
   p.out_raw = static_cast<__nv_bfloat16 *>(dx);
-  return gemm_dispatch_bj<false, true>(dy, w, p, st);
+  p.splits = 1;
+  if (layout == KDCC_LAYOUT_NHWC) {
+    // dx[m][k] = sum_n dy[m][n] w[n][k] : j = k, r = n; W [Nc][K] is j-contiguous -> MN-major B
+    p.I = (int)M; p.J = K; p.R = Nc; p.batch = 1;
+    return gemm_dispatch_bj<false, true>(dy, w, p, st);
+  }
+  // NCHW: dx_b[k][pix] = sum_n w[n][k] dy_b[n][pix] : A(i = k, r = n) = w (i-contiguous, MN-major, shared), B = dy_b (MN-major)
+  const int P = (int)(M / batch);
+  p.I = K; p.J = P; p.R = Nc; p.batch = batch; p.a_batched = 0; p.b_batched = 1;
+  p.out_batch_stride = (long)K * P;
+  return gemm_dispatch_bj<true, true>(w, dy, p, st);
 }
+
+static int dw_bj(int K) { return (K >= 256 && K % 256 == 0) ? 256 : (K > 64 ? 128 : 64); }
 
 int pw_sm100_dw_splits(long M, int K, int Nc) {
-  const int bj = (K >= 256 && K % 256 == 0) ? 256 : (K > 64 ? 128 : 64);
-  const long tiles = (long)ceil_div(Nc, GEMM_BI) * ceil_div(K, bj);
+  const long tiles = (long)ceil_div(Nc, GEMM_BI) * ceil_div(K, dw_bj(K));
   const long rblocks = ceil_div<long>(M, GEMM_BR);
   long s = min(max(1L, (long)kNumSMs / tiles), rblocks);
   const long per = ceil_div<long>(rblocks, s);
   return (int)ceil_div<long>(rblocks, per);  // every split owns at least one reduction block
 }
 
-int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long M, int K, int Nc, cudaStream_t st) {
-  // dw[n][k] = sum_m dy[m][n] x[m][k] : i = n, j = k, r = m; both operands are MN-major views
+int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long M, int K, int Nc, int batch, int layout,
+                    cudaStream_t st) {
+  // dw[n][k] = sum_m dy[m][n] x[m][k] : i = n, j = k, r = pixels
   GemmParams p{};
-  p.I = Nc; p.J = K; p.R = (int)M;
-  p.splits = pw_sm100_dw_splits(M, K, Nc);
-  p.out_f32 = p.splits == 1 ? dw : part;
-  int rc = gemm_dispatch_bj<true, true>(dy, x, p, st);
+  p.I = Nc; p.J = K;
+  int rc;
+  if (layout == KDCC_LAYOUT_NHWC) {
+    p.R = (int)M; p.batch = 1;
+    p.splits = pw_sm100_dw_splits(M, K, Nc);
+    p.out_f32 = p.splits == 1 ? dw : part;
+    rc = gemm_dispatch_bj<true, true>(dy, x, p, st);   // both operands are MN-major views
+  } else {
+    // NCHW: the pixel axis is contiguous in both dy_b [Nc][P] and x_b [K][P]: two K-major operands, the
+    // reduction runs over (image, pixel block)
+    const int P = (int)(M / batch);
+    p.R = P; p.batch = batch; p.a_batched = 1; p.b_batched = 1; p.r_spans_batch = 1;
+    const long rblocks = (long)batch * ceil_div(P, GEMM_BR);
+    const long tiles = (long)ceil_div(Nc, GEMM_BI) * ceil_div(K, dw_bj(K));
+    long s = min(max(1L, (long)kNumSMs / tiles), rblocks);
+    const long per = ceil_div<long>(rblocks, s);
+    p.splits = (int)ceil_div<long>(rblocks, per);
+    p.out_f32 = p.splits == 1 ? dw : part;
+    rc = gemm_dispatch_bj<false, false>(dy, x, p, st);
+  }
   if (rc || p.splits == 1) return rc;
   const long count = (long)Nc * K;  // multiple of 4 because K % 8 == 0
   reduce_splits_kernel<<<(unsigned)ceil_div<long>(count / 4, 256), 256, 0, st>>>(part, dw, p.splits, count);

@@ -5,12 +5,14 @@
 namespace kdcc {
 
 // ---- tcgen05 / TMEM / TMA bf16 GEMMs: pw_gemm_sm100.cu ---------------------------------------------
-bool pw_sm100_supported(long M, int K, int Nc);
+// layout NHWC: x [M][K]; layout NCHW: x [batch][K][M / batch] (the 1x1 conv then runs as W . X per image)
+bool pw_sm100_supported(long M, int K, int Nc, int batch, int layout);
 int pw_sm100_fwd(const void *x, const void *w, const float *scale, const float *shift, int relu, void *y_raw,
-                 void *y_act, long M, int K, int Nc, cudaStream_t st);
-int pw_sm100_bwd_dx(const void *dy, const void *w, void *dx, long M, int K, int Nc, cudaStream_t st);
-int pw_sm100_dw_splits(long M, int K, int Nc);
-int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long M, int K, int Nc, cudaStream_t st);
+                 void *y_act, long M, int K, int Nc, int batch, int layout, cudaStream_t st);
+int pw_sm100_bwd_dx(const void *dy, const void *w, void *dx, long M, int K, int Nc, int batch, int layout, cudaStream_t st);
+int pw_sm100_dw_splits(long M, int K, int Nc);  // upper bound on the split count for either layout
+int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long M, int K, int Nc, int batch, int layout,
+                    cudaStream_t st);
 __global__ void reduce_splits_kernel(const float *__restrict__ part, float *__restrict__ out, int splits, long count);
 
 // ---- CUDA-core GEMM (fp32 parity path, shapes the tensor-core kernel does not take): pw_gemm_simt.cu -

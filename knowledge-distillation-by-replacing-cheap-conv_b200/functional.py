@@ -52,6 +52,21 @@ def _empty_nhwc(n, c, h, w, like):
     return torch.empty((n, c, h, w), dtype=like.dtype, device=like.device, memory_format=torch.channels_last)
 
 
+def _is_plain_nchw(t):
+    """True for a dense NCHW tensor that is not also a valid channels_last view."""
+    return t.dim() == 4 and t.is_contiguous() and not t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _format(t, layout):
+    return t.contiguous() if layout == _abi.NCHW else _nhwc(t)
+
+
+def _empty_like_layout(n, c, h, w, like, layout):
+    if layout == _abi.NCHW:
+        return torch.empty((n, c, h, w), dtype=like.dtype, device=like.device)
+    return _empty_nhwc(n, c, h, w, like)
+
+
 def cast_weight(w_f32, dtype):
     """fp32 master parameter -> activation dtype through kdcc_cast_f32_to_bf16 (no torch arithmetic)."""
     if dtype == torch.float32:
@@ -69,33 +84,39 @@ class _DepthwiseConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, k, dil, pad):
         _require_cuda(x, weight, bias)
-        x = _nhwc(x)
         N, C, H, W = x.shape
         Ho, Wo = H + 2 * pad - dil * (k - 1), W + 2 * pad - dil * (k - 1)
+        code = _dtype_code(x)
+        # the reference's own NCHW layout runs on the tensor-core kernels (bf16); channels_last and fp32 run NHWC
+        layout = _abi.NHWC
+        if _is_plain_nchw(x) and bias is None and \
+                _abi.dispatch_name(0, N, H, W, C, C, k, dil, pad, _abi.NCHW, code) != "unsupported":
+            layout = _abi.NCHW
+        x = _format(x, layout)
         w = weight.detach().reshape(C, k * k).float().contiguous()
         b = bias.detach().float().contiguous() if bias is not None else None
-        y = _empty_nhwc(N, C, Ho, Wo, x)
-        _abi.check(_abi.lib().kdcc_dw_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), N, H, W, C, k, dil, pad,
-                                          _dtype_code(x), _stream()), "kdcc_dw_fwd")
+        y = _empty_like_layout(N, C, Ho, Wo, x, layout)
+        _abi.check(_abi.lib().kdcc_dw_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), N, H, W, C, k, dil, pad, layout,
+                                          code, _stream()), "kdcc_dw_fwd")
         ctx.save_for_backward(x, w)
-        ctx.geom = (k, dil, pad, bias is not None, weight.shape)
+        ctx.geom = (k, dil, pad, bias is not None, weight.shape, layout)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        k, dil, pad, has_bias, wshape = ctx.geom
+        k, dil, pad, has_bias, wshape, layout = ctx.geom
         N, C, H, W = x.shape
-        dy = _nhwc(dy)
+        dy = _format(dy, layout)
         need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
-        dx = _empty_nhwc(N, C, H, W, x) if need_dx else None
+        dx = _empty_like_layout(N, C, H, W, x, layout) if need_dx else None
         dw = torch.empty((C, k * k), dtype=torch.float32, device=x.device) if need_dw else None
         db = torch.empty((C,), dtype=torch.float32, device=x.device) if need_db else None
         L = _abi.lib()
         code = _dtype_code(x)
-        ws = _workspace(L.kdcc_dw_bwd_workspace_bytes(N, H, W, C, k, dil, pad, code), x.device)
+        ws = _workspace(L.kdcc_dw_bwd_workspace_bytes(N, H, W, C, k, dil, pad, layout, code), x.device)
         _abi.check(L.kdcc_dw_bwd(_ptr(x), _ptr(w), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), ws.numel(),
-                                 N, H, W, C, k, dil, pad, code, _stream()), "kdcc_dw_bwd")
+                                 N, H, W, C, k, dil, pad, layout, code, _stream()), "kdcc_dw_bwd")
         return dx, (dw.reshape(wshape) if need_dw else None), db, None, None, None
 
 
@@ -111,12 +132,16 @@ class _PointwiseConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, scale, shift, relu):
         _require_cuda(x, weight, bias)
-        x = _nhwc(x)
         N, K, H, W = x.shape
         Co = weight.shape[0]
         M = N * H * W
+        code = _dtype_code(x)
+        layout = _abi.NHWC
+        if _is_plain_nchw(x) and _abi.dispatch_name(2, N, H, W, K, Co, 1, 1, 0, _abi.NCHW, code) != "unsupported":
+            layout = _abi.NCHW
+        x = _format(x, layout)
         w = cast_weight(weight.detach().reshape(Co, K), x.dtype)
-        y = _empty_nhwc(N, Co, H, W, x)
+        y = _empty_like_layout(N, Co, H, W, x, layout)
         fused = scale is not None or shift is not None or relu
         eff_shift = shift
         if bias is not None and not fused:
@@ -126,38 +151,39 @@ class _PointwiseConv(torch.autograd.Function):
         use_act = fused or bias is not None
         _abi.check(_abi.lib().kdcc_pw_fwd(_ptr(x), _ptr(w), _ptr(scale), _ptr(eff_shift), int(bool(relu)),
                                           None if use_act else _ptr(y), _ptr(y) if use_act else None,
-                                          M, K, Co, _dtype_code(x), _stream()), "kdcc_pw_fwd")
+                                          M, K, Co, N, layout, code, _stream()), "kdcc_pw_fwd")
         if fused:
             ctx.mark_non_differentiable(y)  # inference-only epilogue (eval-mode BN fold)
         ctx.save_for_backward(x, w)
-        ctx.meta = (bias is not None, weight.shape)
+        ctx.meta = (bias is not None, weight.shape, layout)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        has_bias, wshape = ctx.meta
+        has_bias, wshape, layout = ctx.meta
         N, K, H, W = x.shape
         Co = w.shape[0]
         M = N * H * W
-        dy = _nhwc(dy)
+        dy = _format(dy, layout)
         L = _abi.lib()
         code = _dtype_code(x)
         st = _stream()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _empty_nhwc(N, K, H, W, x)
-            _abi.check(L.kdcc_pw_bwd_dx(_ptr(dy), _ptr(w), _ptr(dx), None, 0, M, K, Co, code, st), "kdcc_pw_bwd_dx")
+            dx = _empty_like_layout(N, K, H, W, x, layout)
+            _abi.check(L.kdcc_pw_bwd_dx(_ptr(dy), _ptr(w), _ptr(dx), None, 0, M, K, Co, N, layout, code, st), "kdcc_pw_bwd_dx")
         if ctx.needs_input_grad[1]:
             dw = torch.empty((Co, K), dtype=torch.float32, device=x.device)
             ws = _workspace(L.kdcc_pw_bwd_workspace_bytes(1, M, K, Co, code), x.device)
-            _abi.check(L.kdcc_pw_bwd_dw(_ptr(dy), _ptr(x), _ptr(dw), _ptr(ws), ws.numel(), M, K, Co, code, st),
+            _abi.check(L.kdcc_pw_bwd_dw(_ptr(dy), _ptr(x), _ptr(dw), _ptr(ws), ws.numel(), M, K, Co, N, layout, code, st),
                        "kdcc_pw_bwd_dw")
             dw = dw.reshape(wshape)
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty((Co,), dtype=torch.float32, device=x.device)
+            dyr = _nhwc(dy)  # column sums are taken over the pixel-major view
             ws = _workspace(L.kdcc_colsum_workspace_bytes(M, Co), x.device)
-            _abi.check(L.kdcc_colsum(_ptr(dy), _ptr(db), _ptr(ws), ws.numel(), M, Co, code, st), "kdcc_colsum")
+            _abi.check(L.kdcc_colsum(_ptr(dyr), _ptr(db), _ptr(ws), ws.numel(), M, Co, code, st), "kdcc_colsum")
         return dx, dw, db, None, None, None
 
 

@@ -47,7 +47,7 @@ class EventLog:
 class HotPathStep:
     def __init__(self, plan, batch, height, width, kernel_size=9, dilation=5, padding=20, dtype=torch.bfloat16,
                  device="cuda", logits_shape=None, kd_temperature=1.0, hint_num_classes=1000.0,
-                 accumulation_steps=1, kd_grad=False, need_dx=True, seed=0):
+                 accumulation_steps=1, kd_grad=False, need_dx=True, seed=0, layout="nchw"):
         self.plan = list(plan)
         self.N, self.H, self.W = batch, height, width
         self.k, self.d, self.p = kernel_size, dilation, padding
@@ -57,6 +57,8 @@ class HotPathStep:
         self.code = _abi.F32 if dtype == torch.float32 else _abi.BF16
         self.T, self.nc, self.acc_steps = float(kd_temperature), float(hint_num_classes), int(accumulation_steps)
         self.kd_grad, self.need_dx = kd_grad, need_dx
+        # "nchw" = the reference's layout -> tensor-core depthwise + W.X pointwise; "nhwc" = channels-last kernels
+        self.layout = _abi.NCHW if layout == "nchw" else _abi.NHWC
         self.L = _abi.lib()
         kk = kernel_size * kernel_size
 
@@ -82,7 +84,10 @@ class HotPathStep:
         cmax = max(ci for ci, _ in self.plan)
         omax = max(co for _, co in self.plan)
         n = batch
-        e = lambda c, h, w: torch.empty((n, h, w, c), dtype=dtype, device=self.device)
+        if self.layout == _abi.NCHW:
+            e = lambda c, h, w: torch.empty((n, c, h, w), dtype=dtype, device=self.device)
+        else:
+            e = lambda c, h, w: torch.empty((n, h, w, c), dtype=dtype, device=self.device)
         # scratch shared by all sites (each site's forward+backward completes before the next starts)
         self.mid = e(cmax, self.Ho, self.Wo)
         self.dmid = e(cmax, self.Ho, self.Wo)
@@ -93,7 +98,7 @@ class HotPathStep:
         ws_bytes = self.L.kdcc_loss_workspace_bytes()
         for ci, co in self.plan:
             M = n * self.Ho * self.Wo
-            ws_bytes = max(ws_bytes, self.L.kdcc_dw_bwd_workspace_bytes(n, height, width, ci, self.k, self.d, self.p, self.code),
+            ws_bytes = max(ws_bytes, self.L.kdcc_dw_bwd_workspace_bytes(n, height, width, ci, self.k, self.d, self.p, self.layout, self.code),
                            self.L.kdcc_pw_bwd_workspace_bytes(1, M, ci, co, self.code))
         self.ws = torch.empty(ws_bytes + 64, dtype=torch.uint8, device=self.device)
         self.hint_losses = torch.zeros(len(self.plan), dtype=torch.float32, device=self.device)
@@ -111,8 +116,12 @@ class HotPathStep:
             t = (torch.randn(shape, generator=g) * scale).to(dtype)
             return t.pin_memory() if pinned_host else t.to(self.device)
 
-        xs = [rnd((self.N, self.H, self.W, ci), self.dtype) for ci, _ in self.plan]
-        ts = [rnd((self.N, self.Ho, self.Wo, co), self.dtype) for _, co in self.plan]
+        if self.layout == _abi.NCHW:
+            xs = [rnd((self.N, ci, self.H, self.W), self.dtype) for ci, _ in self.plan]
+            ts = [rnd((self.N, co, self.Ho, self.Wo), self.dtype) for _, co in self.plan]
+        else:
+            xs = [rnd((self.N, self.H, self.W, ci), self.dtype) for ci, _ in self.plan]
+            ts = [rnd((self.N, self.Ho, self.Wo, co), self.dtype) for _, co in self.plan]
         ls = lt = None
         if self.logits_shape:
             ls, lt = rnd(self.logits_shape, torch.float32, 3.0), rnd(self.logits_shape, torch.float32, 3.0)
@@ -124,7 +133,7 @@ class HotPathStep:
 
     def step(self, xs, teacher_feats, logits_s=None, logits_t=None, log=None):
         """One pass; returns (hint_loss_sum, kd_loss) as 0-dim device tensors (no host sync)."""
-        L, st, code, n = self.L, _stream(), self.code, self.N
+        L, st, code, n, lay = self.L, _stream(), self.code, self.N, self.layout
         H, W, Ho, Wo, k, d, p = self.H, self.W, self.Ho, self.Wo, self.k, self.d, self.p
         chk = _abi.check
         ws, wsn = _ptr(self.ws), self.ws.numel()
@@ -141,19 +150,19 @@ class HotPathStep:
                 chk(L.kdcc_cast_f32_to_bf16(_ptr(w_pw), _ptr(w_lp), co * ci, st), "cast")
                 mark("cast_w")
                 launches += 1
-            chk(L.kdcc_dw_fwd(_ptr(x), _ptr(w_dw), None, _ptr(self.mid), n, H, W, ci, k, d, p, code, st), "dw_fwd")
+            chk(L.kdcc_dw_fwd(_ptr(x), _ptr(w_dw), None, _ptr(self.mid), n, H, W, ci, k, d, p, lay, code, st), "dw_fwd")
             mark("dw_fwd")
-            chk(L.kdcc_pw_fwd(_ptr(self.mid), _ptr(w_lp), None, None, 0, _ptr(self.y), None, M, ci, co, code, st), "pw_fwd")
+            chk(L.kdcc_pw_fwd(_ptr(self.mid), _ptr(w_lp), None, None, 0, _ptr(self.y), None, M, ci, co, n, lay, code, st), "pw_fwd")
             mark("pw_fwd")
             chk(L.kdcc_hint_loss(_ptr(self.y), _ptr(tf), None, 0, _ptr(self.dy), _ptr(self.hint_losses[i:]), ws, wsn,
-                                 n, co, Ho * Wo, _abi.NHWC, self.nc, code, 1.0 / self.acc_steps, st), "hint_loss")
+                                 n, co, Ho * Wo, lay, self.nc, code, 1.0 / self.acc_steps, st), "hint_loss")
             mark("hint_loss")
-            chk(L.kdcc_pw_bwd_dw(_ptr(self.dy), _ptr(self.mid), _ptr(g_pw), ws, wsn, M, ci, co, code, st), "pw_bwd_dw")
+            chk(L.kdcc_pw_bwd_dw(_ptr(self.dy), _ptr(self.mid), _ptr(g_pw), ws, wsn, M, ci, co, n, lay, code, st), "pw_bwd_dw")
             mark("pw_bwd_dw")
-            chk(L.kdcc_pw_bwd_dx(_ptr(self.dy), _ptr(w_lp), _ptr(self.dmid), None, 0, M, ci, co, code, st), "pw_bwd_dx")
+            chk(L.kdcc_pw_bwd_dx(_ptr(self.dy), _ptr(w_lp), _ptr(self.dmid), None, 0, M, ci, co, n, lay, code, st), "pw_bwd_dx")
             mark("pw_bwd_dx")
             chk(L.kdcc_dw_bwd(_ptr(x), _ptr(w_dw), _ptr(self.dmid), _ptr(self.dx) if self.need_dx else None, _ptr(g_dw),
-                              None, ws, wsn, n, H, W, ci, k, d, p, code, st), "dw_bwd")
+                              None, ws, wsn, n, H, W, ci, k, d, p, lay, code, st), "dw_bwd")
             mark("dw_bwd")
             # dw_fwd 1, pw_fwd 1, hint 2 (pass + finalize), pw_dw 2 (gemm + split reduce), pw_dx 1,
             # dw_bwd: wgrad 1 + reduce 1 (+ dx conv 1)

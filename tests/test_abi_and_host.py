@@ -36,26 +36,35 @@ def test_library_exports_every_declared_symbol(kdcc):
 
 def test_version_and_error_strings(kdcc):
     L = kdcc._abi.lib()
-    assert L.kdcc_version() == 100
+    assert L.kdcc_version() == 101
     assert "success" in kdcc._abi.strerror(0)
     for code in (-1, -2, -3, -4, -5):
         assert kdcc._abi.strerror(code).startswith("kdcc:")
     assert L.kdcc_loss_workspace_bytes() > 0
     # argument validation happens before any CUDA call, so it is testable without a GPU
-    assert L.kdcc_dw_fwd(None, None, None, None, 1, 8, 8, 16, 3, 1, 1, 1, None) == -1
-    assert L.kdcc_dw_fwd(None, None, None, None, 1, 8, 8, 6, 3, 1, 1, 1, None) == -2     # C % 8
-    assert L.kdcc_pw_fwd(None, None, None, None, 0, None, None, 128, 64, 64, 7, None) == -1  # bad dtype
-    assert L.kdcc_dw_bwd_workspace_bytes(1, 128, 128, 512, 9, 5, 20, 1) > 0
+    assert L.kdcc_dw_fwd(None, None, None, None, 1, 8, 8, 16, 3, 1, 1, 0, 1, None) == -1
+    assert L.kdcc_dw_fwd(None, None, None, None, 1, 8, 8, 6, 3, 1, 1, 0, 1, None) == -2     # C % 8 (NHWC)
+    assert L.kdcc_dw_fwd(None, None, None, None, 1, 8, 8, 6, 3, 1, 1, 1, 0, None) == -2     # NCHW is bf16-only
+    assert L.kdcc_pw_fwd(None, None, None, None, 0, None, None, 128, 64, 64, 1, 0, 7, None) == -1  # bad dtype
+    assert L.kdcc_dw_bwd_workspace_bytes(1, 128, 128, 512, 9, 5, 20, 0, 1) > 0
+    assert L.kdcc_dw_bwd_workspace_bytes(1, 128, 128, 512, 9, 5, 20, 1, 1) > 0
 
 
 def test_dispatch_names(kdcc):
     d = kdcc._abi.dispatch_name
-    assert d(0, 1, 128, 128, 512, 512, 9, 5, 20, kdcc._abi.BF16) == "dw_conv_tma_k9"
-    assert d(1, 1, 128, 128, 512, 512, 9, 5, 20, kdcc._abi.BF16) == "dw_wgrad_tma_k9"
-    assert d(0, 32, 8, 8, 64, 64, 3, 1, 1, kdcc._abi.BF16) == "dw_conv_tma_k3"
-    assert d(0, 1, 128, 128, 512, 512, 9, 5, 20, kdcc._abi.F32) == "dw_direct"
-    assert d(2, 1, 128, 128, 512, 512, 9, 5, 20, kdcc._abi.BF16) == "pw_gemm_sm100_tn"
-    assert d(2, 1, 128, 128, 512, 512, 9, 5, 20, kdcc._abi.F32) == "pw_simt"
+    NHWC, NCHW, BF16, F32 = kdcc._abi.NHWC, kdcc._abi.NCHW, kdcc._abi.BF16, kdcc._abi.F32
+    assert d(0, 1, 128, 128, 512, 512, 9, 5, 20, NHWC, BF16) == "dw_conv_tma_k9"
+    assert d(1, 1, 128, 128, 512, 512, 9, 5, 20, NHWC, BF16) == "dw_wgrad_tma_k9"
+    assert d(0, 32, 8, 8, 64, 64, 3, 1, 1, NHWC, BF16) == "dw_conv_tma_k3"
+    assert d(0, 1, 128, 128, 512, 512, 9, 5, 20, NHWC, F32) == "dw_direct"
+    assert d(2, 1, 128, 128, 512, 512, 9, 5, 20, NHWC, BF16) == "pw_gemm_sm100_fwd"
+    assert d(2, 1, 128, 128, 512, 512, 9, 5, 20, NHWC, F32) == "pw_simt"
+    # the reference's NCHW layout: depthwise on the tensor cores, pointwise as W.X per image
+    assert d(0, 1, 128, 128, 512, 512, 9, 5, 20, NCHW, BF16) == "dw_tc_conv"
+    assert d(1, 1, 128, 128, 512, 512, 9, 5, 20, NCHW, BF16) == "dw_tc_wgrad"
+    assert d(2, 1, 128, 128, 512, 512, 9, 5, 20, NCHW, BF16) == "pw_gemm_sm100_fwd"
+    assert d(0, 1, 128, 128, 512, 512, 9, 5, 20, NCHW, F32) == "unsupported"
+    assert d(0, 1, 30, 30, 16, 16, 3, 1, 1, NCHW, BF16) == "unsupported"       # W % 8 != 0 -> channels_last path
 
 
 def test_block_keeps_reference_interface(kdcc):

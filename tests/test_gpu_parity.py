@@ -19,9 +19,9 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-def to_dev(a, dtype, grad=False):
+def to_dev(a, dtype, grad=False, layout="nhwc"):
     t = torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dtype)
-    if t.dim() == 4:
+    if t.dim() == 4 and layout == "nhwc":
         t = t.contiguous(memory_format=torch.channels_last)
     return t.requires_grad_(grad)
 
@@ -35,15 +35,18 @@ def q(a, dtype):
     return host(torch.from_numpy(np.ascontiguousarray(a)).to(dtype))
 
 
-def run_block(kdcc, x, w_dw, w_pw, dy, k, d, p, dtype):
+def run_block(kdcc, x, w_dw, w_pw, dy, k, d, p, dtype, layout="nhwc"):
     Ci, Co = w_dw.shape[0], w_pw.shape[0]
     blk = kdcc.DepthwiseSeparableBlock(Ci, Co, k, p, d, Ci, None).cuda()
     with torch.no_grad():
         blk.separable_conv.weight.copy_(torch.from_numpy(w_dw))
         blk.pointwise_conv.weight.copy_(torch.from_numpy(w_pw))
-    xt = to_dev(x, dtype, grad=True)
+    xt = to_dev(x, dtype, grad=True, layout=layout)
     y = blk(xt)
-    y.backward(to_dev(dy, dtype))
+    if layout == "nchw":  # the tensor-core path keeps the reference's layout end to end
+        assert y.is_contiguous() and not (y.dim() == 4 and y.shape[1] > 1 and y.shape[2] * y.shape[3] > 1 and
+                                          y.is_contiguous(memory_format=torch.channels_last))
+    y.backward(to_dev(dy, dtype, layout=layout))
     torch.cuda.synchronize()
     return host(y), host(xt.grad), host(blk.separable_conv.weight.grad), host(blk.pointwise_conv.weight.grad)
 
@@ -116,6 +119,74 @@ def test_block_matches_oracle_seeded(kdcc, geom, dtype):
     ry, rdx, rdwd, rdwp = oracle_block(x, w_dw, w_pw, dy, k, d, p, dtype)
     for name, mine, ref in (("y", y, ry), ("dx", dx, rdx), ("dw_dw", dwd, rdwd), ("dw_pw", dwp, rdwp)):
         assert relerr(mine, ref) < TOL[dtype], name
+
+
+SEEDED_NCHW = [
+    # N, Ci, Co,   H,   W, k, d,  p      (W % 8 == 0: rows are 16-byte multiples for TMA)
+    (2, 64, 128, 40, 40, 9, 5, 20),     # Cityscapes geometry, one partial 128x128 tile per plane
+    (1, 16, 32, 136, 200, 9, 5, 20),    # 2 x 2 tiles with real halos between them, ragged edges
+    (32, 64, 64, 8, 8, 3, 1, 1),        # CIFAR ResNet44 layer3 block shape (N-tile 32 path)
+    (1, 384, 384, 32, 32, 9, 5, 20),    # HRNet-OCR site shape
+    (2, 8, 8, 24, 16, 5, 2, 4),         # 5x5 dilated
+    (1, 16, 16, 16, 24, 7, 1, 3),       # 7x7
+    (2, 8, 16, 20, 24, 5, 2, 0),        # no padding: output (12 x 16) smaller than input
+    (1, 512, 512, 128, 128, 9, 5, 20),  # one full-size 51M-plan site
+]
+
+
+@pytest.mark.parametrize("geom", SEEDED_NCHW)
+def test_block_nchw_tensor_core_matches_oracle(kdcc, geom):
+    N, Ci, Co, H, W, k, d, p = geom
+    dtype = torch.bfloat16
+    rs = np.random.RandomState(4321 + Ci + H)
+    x = rs.standard_normal((N, Ci, H, W)).astype(np.float32)
+    w_dw = (rs.uniform(-1, 1, (Ci, 1, k, k)) / k).astype(np.float32)
+    w_pw = (rs.uniform(-1, 1, (Co, Ci, 1, 1)) / np.sqrt(Ci)).astype(np.float32)
+    Ho, Wo = H + 2 * p - d * (k - 1), W + 2 * p - d * (k - 1)
+    dy = rs.standard_normal((N, Co, Ho, Wo)).astype(np.float32)
+    assert kdcc._abi.dispatch_name(0, N, H, W, Ci, Co, k, d, p, kdcc._abi.NCHW, kdcc._abi.BF16) == "dw_tc_conv"
+    y, dx, dwd, dwp = run_block(kdcc, x, w_dw, w_pw, dy, k, d, p, dtype, layout="nchw")
+    # the tensor-core depthwise multiplies bf16-rounded taps (the Toeplitz operand), so the oracle gets them too
+    ry, rdx, rdwd, rdwp = oracle_block(x, q(w_dw, dtype), w_pw, dy, k, d, p, dtype)
+    for name, mine, ref in (("y", y, ry), ("dx", dx, rdx), ("dw_dw", dwd, rdwd), ("dw_pw", dwp, rdwp)):
+        assert relerr(mine, ref) < TOL[dtype], name
+
+
+def test_block_nchw_golden_cifar(kdcc, golden_block):
+    g, tag = golden_block, "cifar_k3"
+    N, Ci, Co, H, W, k, d, p = [int(v) for v in g[f"{tag}/geom"]]
+    y, dx, dwd, dwp = run_block(kdcc, g[f"{tag}/x"], g[f"{tag}/w_dw"], g[f"{tag}/w_pw"], g[f"{tag}/dy"], k, d, p,
+                                torch.bfloat16, layout="nchw")
+    for name, mine in (("y", y), ("dx", dx), ("dw_dw", dwd), ("dw_pw", dwp)):
+        assert relerr(mine, g[f"{tag}/{name}"]) < TOL[torch.bfloat16], name
+
+
+def test_full_size_nchw_impulse_adjoint(kdcc):
+    """NCHW tensor-core depthwise at the 51M-plan size: impulse response = mirrored taps; forward, input-gradient
+    and weight-gradient kernels satisfy the adjoint identities."""
+    torch.manual_seed(5)
+    C, H, W, k, d, p = 512, 128, 128, 9, 5, 20
+    w = (torch.randn(C, 1, k, k, device="cuda") / k).to(torch.bfloat16).float().requires_grad_(True)
+    x = torch.zeros(1, C, H, W, device="cuda", dtype=torch.bfloat16)
+    x[0, :, 64, 70] = 1.0
+    y = kdcc.functional.depthwise_conv(x, w, None, k, d, p)
+    assert y.is_contiguous()
+    expect = torch.zeros(1, C, H, W, device="cuda")
+    for u in range(k):
+        for v in range(k):
+            i, j = 64 - u * d + p, 70 - v * d + p
+            if 0 <= i < H and 0 <= j < W:
+                expect[0, :, i, j] = w.detach()[:, 0, u, v]
+    assert torch.equal(y.float(), expect.to(torch.bfloat16).float())
+    a = torch.randn(2, C, H, W, device="cuda", dtype=torch.bfloat16).requires_grad_(True)
+    g = torch.randn(2, C, H, W, device="cuda", dtype=torch.bfloat16)
+    ya = kdcc.functional.depthwise_conv(a, w, None, k, d, p)
+    ya.backward(g)
+    lhs = (ya.double() * g.double()).sum()
+    mid = (a.detach().double() * a.grad.double()).sum()
+    rhs = (w.detach().double() * w.grad.double()).sum()
+    assert abs(lhs - mid) / abs(lhs) < 1e-2
+    assert abs(lhs - rhs) / abs(lhs) < 1e-2
 
 
 GEMMS = [(4096, 512, 512), (2048, 1024, 2048), (1024, 4096, 256), (2000, 72, 24), (128 * 5 + 8, 64, 64), (300, 384, 384)]

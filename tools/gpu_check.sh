@@ -15,6 +15,7 @@ run block_bf16_direct 300 "bf16_matches_reference_golden and direct"
 run block_bf16_plain_load 300 "bf16_matches_reference_golden and tma_plain_load"
 run block_bf16_plain_store 300 "bf16_matches_reference_golden and tma_plain_store"
 run block_bf16_tma 300 "bf16_matches_reference_golden and tma and not plain"
+run nchw 600 "nchw"
 run gemm 400 "gemm or epilogue"
 run seeded 600 "seeded"
 run full_size 600 "full_size or errors"
