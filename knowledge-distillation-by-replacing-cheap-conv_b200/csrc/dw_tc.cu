@@ -66,14 +66,32 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, int base_mode = 1) {
   return d;
 }
 
-template <int NT>
+// 64-bit descriptors are assembled from 32-bit halves inside the asm so that the single issuing thread spends
+// one integer add per operand per MMA (the MMAs are small -- N = 16/32 -- and would otherwise be issue-bound).
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int NT, int KS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const int a_stage_bytes = p.nbox * p.box_bytes;
-  constexpr int BU_BYTES = NT * 128;                 // one tap row's Toeplitz tile
+  // one tap row's Toeplitz tile, un-swizzled K-major core matrices: [K chunk of 8][NT rows][16 bytes]
+  constexpr int BU_BYTES = KS * 2 * NT * 16;
   const int b_stage_bytes = p.k * BU_BYTES;
   const int AS = p.a_stages;
   const uint32_t b_base = smem_base + AS * a_stage_bytes;
@@ -134,6 +152,21 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
     // ===== MMA issuer =====
     // instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, N = NT, M = 128
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+    constexpr int T = TC_TILE / NT;
+    // A: K-major SWIZZLE_128B (SBO 1024, version 1); the start may sit on any 128-byte row / 32-byte K slice of the
+    // window: the hardware derives the swizzle phase from the address bits, the base-offset field stays 0.
+    const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    // B: K-major, no swizzle: 8-row groups 128 B apart (SBO), K chunks NT*16 B apart (LBO)
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t b_lbo = (uint32_t)((NT * 16) >> 4) << 16;
+    uint32_t a_off[T][KS];  // descriptor start-address increments (16-byte units) of every (N-tile, K slice)
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const int q0 = t * NT + kk * 16;  // first window column of this 16-wide reduction slice
+        a_off[t][kk] = ((uint32_t)(q0 >> 6) * (uint32_t)p.box_bytes + (uint32_t)(q0 & 63) * 2u) >> 4;
+      }
     int it = 0;
     int as = 0; uint32_t aph = 0;
     for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
@@ -143,20 +176,21 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
       ptx::mbar_wait(b_full(s), ph);
       const uint32_t b0 = b_base + s * b_stage_bytes;
       const uint32_t d0 = tmem_base + (uint32_t)(s * TC_TILE);
+#pragma unroll 1
       for (int u = 0; u < p.k; ++u) {
         if (!p.single || u == 0) ptx::mbar_wait(a_full(as), aph);
         ptx::tcgen05_fence_after();
-        // single window: tap row u starts u*dil rows further down the same tile
+        // single window: tap row u starts u*dil rows (128 B each) further down the same tile
         const uint32_t a0 = smem_base + as * a_stage_bytes + (p.single ? (uint32_t)(u * p.dil) * 128u : 0u);
-        const uint32_t b_u = b0 + (uint32_t)u * BU_BYTES;
-#pragma unroll 1
-        for (int t = 0; t < TC_TILE / NT; ++t) {
-          for (int kk = 0; kk < p.ksteps; ++kk) {
-            const int q0 = t * NT + kk * 16;  // first window column of this 16-wide reduction slice
-            const uint32_t a_addr = a0 + (uint32_t)(q0 >> 6) * (uint32_t)p.box_bytes + (uint32_t)(q0 & 63) * 2u;
-            ptx::umma_f16(d0 + (uint32_t)(t * NT), tc_desc(a_addr, p.dbg), tc_desc(b_u + kk * 32), idesc, (u | kk) ? 1u : 0u);
-          }
-        }
+        const uint32_t a_lo = ((a0 & 0x3FFFF) >> 4) | (1u << 16);
+        const uint32_t b_lo = (((b0 + (uint32_t)u * BU_BYTES) & 0x3FFFF) >> 4) | b_lbo;
+        const uint32_t acc0 = u ? 1u : 0u;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int kk = 0; kk < KS; ++kk)
+            tc_mma(d0 + (uint32_t)(t * NT), a_lo + a_off[t][kk], a_hi, b_lo + (uint32_t)(kk * 2 * NT), b_hi, idesc,
+                   kk ? 1u : acc0);
         if (!p.single || u == p.k - 1) {
           ptx::umma_commit(a_empty(as));  // tile free once these MMAs have read it
           if (++as == AS) { as = 0; aph ^= 1; }
@@ -185,7 +219,7 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
         const int u = e / (p.k * NT);
         const int jp = j + v * p.dil + p.extra;  // reduction column that feeds output column j through tap v
         const float wv = __ldg(wc + (p.flip ? (p.k - 1 - u) * p.k + (p.k - 1 - v) : u * p.k + v));
-        const int off = u * BU_BYTES + (j >> 3) * 1024 + (j & 7) * 128 + ((((jp >> 3) ^ (j & 7)) & 7) << 4) + (jp & 7) * 2;
+        const int off = u * BU_BYTES + (jp >> 3) * (NT * 16) + j * 16 + (jp & 7) * 2;
         *reinterpret_cast<__nv_bfloat16 *>(bs + off) = __float2bfloat16_rn(wv);
       }
       ptx::fence_proxy_async_smem();
@@ -243,26 +277,28 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
 // host side
 // ------------------------------------------------------------------------------------------------
 static int tc_extra(int pad) { return (8 - pad % 8) % 8; }
-static int tc_nt(int reach) { return reach + 32 <= 64 ? 32 : 16; }  // reach = halo + alignment columns
+// output columns per MMA (N): 32 halves both the MMA count and the A re-reads; the Toeplitz K extent
+// (N + halo + alignment columns) must stay within the instantiated K-slice counts
+static int tc_nt(int reach) { return reach + 32 <= 80 ? 32 : 16; }
 
 bool dw_tc_supported(int Hi, int Wi, int Ho, int Wo, int k, int dil) {
   (void)Hi; (void)Ho;
   const int halo = dil * (k - 1);
   if (k > 9 || k % 2 == 0) return false;      // wgrad keeps k*k register partials: instantiated for k = 1,3,5,7,9
-  if (halo + 7 + 16 > 64) return false;       // one 64-column swizzle group per Toeplitz tile (incl. alignment columns)
+  if (halo + 7 + 16 > 80) return false;       // Toeplitz K extent (incl. alignment columns) <= 5 slices of 16
   if (Wi % 8 != 0 || Wo % 8 != 0) return false;  // 16-byte rows for TMA strides and epilogue stores
   return true;
 }
 
-template <int NT>
+template <int NT, int KS>
 static int tc_conv_launch(const void *in, const DwTcParams &p0, cudaStream_t st) {
   DwTcParams p = p0;
-  p.ksteps = ceil_div(NT + p.halo + p.extra, 16);
-  p.nbox = ceil_div((TC_TILE - NT) + p.ksteps * 16, 64);  // the last N-tile's last reduction slice ends here
+  p.ksteps = KS;
+  p.nbox = ceil_div((TC_TILE - NT) + KS * 16, 64);  // the last N-tile's last reduction slice ends here
   p.rows = TC_TILE + (p.single ? p.halo : 0);
   p.box_bytes = (p.rows + 7) / 8 * 8 * 128;
-  const int b_bytes = 2 * p.k * NT * 128;
-  p.a_stages = min(p.single ? 2 : 8, (int)((220 * 1024 - b_bytes - 1024) / (p.nbox * p.box_bytes)));
+  const int b_bytes = 2 * p.k * KS * 2 * NT * 16;
+  p.a_stages = min(p.single ? 2 : 8, (int)((226 * 1024 - b_bytes - 2048) / (p.nbox * p.box_bytes)));
   if (p.a_stages < 2) return KDCC_ESHAPE;
   CUtensorMap tm;
   const uint64_t dims[4] = {(uint64_t)p.Wi, (uint64_t)p.Hi, (uint64_t)p.C, (uint64_t)p.N};
@@ -273,13 +309,24 @@ static int tc_conv_launch(const void *in, const DwTcParams &p0, cudaStream_t st)
   const int smem = p.a_stages * p.nbox * p.box_bytes + b_bytes + 256 + 1024;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tc_conv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(dw_tc_conv_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     attr_smem = smem;
   }
   const int grid = (int)min(p.items, (long)kNumSMs);
-  dw_tc_conv_kernel<NT><<<grid, TC_THREADS, smem, st>>>(tm, p);
+  dw_tc_conv_kernel<NT, KS><<<grid, TC_THREADS, smem, st>>>(tm, p);
   return launch_status();
+}
+
+template <int NT>
+static int tc_conv_dispatch_ks(const void *in, const DwTcParams &p, cudaStream_t st) {
+  switch (ceil_div(NT + p.halo + p.extra, 16)) {
+    case 1: case 2: return tc_conv_launch<NT, 2>(in, p, st);
+    case 3: return tc_conv_launch<NT, 3>(in, p, st);
+    case 4: return tc_conv_launch<NT, 4>(in, p, st);
+    case 5: return tc_conv_launch<NT, 5>(in, p, st);
+    default: return KDCC_ESHAPE;
+  }
 }
 
 int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int N, int C, int Hi, int Wi, int Ho,
@@ -301,8 +348,8 @@ int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int
   if (TC_TILE + p.halo > 256) p.single = 0;  // TMA box rows
   const char *e = getenv("KDCC_DW_TC_NT");
   const int nt = e ? atoi(e) : tc_nt(p.halo + p.extra);
-  if (nt == 32 && p.halo + p.extra + 32 <= 64) return tc_conv_launch<32>(in, p, st);
-  return tc_conv_launch<16>(in, p, st);
+  if (nt == 32 && p.halo + p.extra + 32 <= 80) return tc_conv_dispatch_ks<32>(in, p, st);
+  return tc_conv_dispatch_ks<16>(in, p, st);
 }
 
 }  // namespace kdcc

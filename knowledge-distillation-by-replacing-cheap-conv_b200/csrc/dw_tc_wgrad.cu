@@ -40,15 +40,22 @@ struct DwTcWgradParams {
   float *out;                       // [splits][C][k*k] (or dw itself when splits == 1)
 };
 
-// MN-major SWIZZLE_128B operand: 64-element groups `lbo` bytes apart, 8-row (reduction) groups 1024 B apart
-__device__ __forceinline__ uint64_t wg_desc(uint32_t addr, uint32_t lbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+// MN-major SWIZZLE_128B operands: 64-element groups LBO bytes apart, 8-row (reduction) groups 1024 B apart.
+// Descriptors are assembled from 32-bit halves inside the asm: one integer add per operand per MMA for the
+// single issuing thread.
+__device__ __forceinline__ void wg_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 constexpr int WG_BOX = WG_TILE * 128;  // 128 rows x 64 columns, swizzled
@@ -150,10 +157,13 @@ dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           const uint32_t d_tmem = tmem_base + (uint32_t)(tb * 256);
           // single window: tap row u starts u*dil rows (128 B each) further down the same tile
           const uint32_t xa = smem_base + xs * x_bytes + (p.single ? (uint32_t)(u * p.dil) * 128u : 0u);
+          // lo halves: start address | LBO; hi half (shared): SBO 1024, version 1, SWIZZLE_128B
+          const uint32_t a_lo = ((dys & 0x3FFFF) >> 4) | ((uint32_t)(WG_BOX >> 4) << 16);
+          const uint32_t b_lo = ((xa & 0x3FFFF) >> 4) | ((uint32_t)(p.box_bytes >> 4) << 16);
+          const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
 #pragma unroll
-          for (int ks = 0; ks < WG_TILE / 16; ++ks)  // 16 reduction rows per MMA = 2 KB in both tiles
-            ptx::umma_f16(d_tmem, wg_desc(dys + ks * 2048, WG_BOX), wg_desc(xa + ks * 2048, (uint32_t)p.box_bytes), idesc,
-                          ks ? 1u : 0u);
+          for (int ks = 0; ks < WG_TILE / 16; ++ks)  // 16 reduction rows per MMA = 2 KB (128 x 16-byte units) in both tiles
+            wg_mma(d_tmem, a_lo + ks * 128, b_lo + ks * 128, hi, idesc, ks ? 1u : 0u);
           ptx::umma_commit(t_full(tb));
           if (!p.single || u == K - 1) {
             ptx::umma_commit(x_empty(xs));
