@@ -9,6 +9,8 @@ from ._abi import KdccError, LIB_PATH
 from .blocks import DepthwiseSeparableBlock
 from .losses import EnsembleKLDivergenceLoss, KLDivergenceLoss, MSELoss, WeightedHintMSELoss
 from . import functional
+from .student import DepthwiseStudent
+from .trainer import ConfusionMatrix, GradBucket, LayerwiseStep
 
-__all__ = ["DepthwiseSeparableBlock", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
+__all__ = ["DepthwiseSeparableBlock", "DepthwiseStudent", "LayerwiseStep", "GradBucket", "ConfusionMatrix", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
            "functional", "KdccError", "LIB_PATH"]

@@ -1,0 +1,108 @@
+"""The layerwise distillation step: loop body of trainer/layerwise_trainer.py:220-250, made sync-free and
+data-parallel.
+
+What is kept from the reference: `model(data)` -> (student, teacher) logits with hint features collected
+by the hooks; supervised / KD / teacher losses computed for logging; the hint loss (sum over the hooked
+pairs, divided by accumulation_steps) is the ONLY loss back-propagated (layerwise_trainer.py:229-235);
+the optimizer steps when `batch_idx % accumulation_steps == 0` (so also on index 0, as in the reference).
+
+What changes: no `.item()`, no `.cpu()` of the logits, no NumPy confusion matrix in the step (SURVEY.md
+F13) -- losses stay 0-dim device tensors and the IoU confusion matrix is accumulated on the GPU; with
+world_size > 1 the trainable student gradients are averaged with ONE all-reduce of a flat bucket (frozen
+teacher replicated, eval-mode BN: no other cross-rank coupling).
+"""
+from functools import reduce
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucket:
+    """Flat fp32 view of the trainable parameters' gradients: one all-reduce per optimizer step.
+    Rebuild it (`GradBucket(params)`) whenever prepare_train_epoch changes the trainable set."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:  # parameters' .grad become views into the bucket: no copies at step time
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            world = dist.get_world_size(group)
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:  # gloo has no AVG
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(world)
+
+
+class ConfusionMatrix:
+    """Device-side replacement of utils/util.py:108-128 (CityscapesMetricTracker): argmax + bincount stay on
+    the GPU, nothing is copied to the host until `iou()` is asked for."""
+
+    def __init__(self, num_classes=19, ignore_index=255, device="cpu"):
+        self.nc, self.ignore = num_classes, ignore_index
+        self.mat = torch.zeros(num_classes * num_classes, dtype=torch.long, device=device)
+
+    def reset(self):
+        self.mat.zero_()
+
+    @torch.no_grad()
+    def update(self, logits, target):
+        pred = logits.argmax(dim=1).reshape(-1)
+        tgt = target.reshape(-1)
+        keep = (tgt != self.ignore) & (tgt >= 0) & (tgt < self.nc)
+        idx = tgt[keep] * self.nc + pred[keep]
+        self.mat += torch.bincount(idx, minlength=self.nc * self.nc).to(self.mat.device)
+
+    def iou(self):
+        m = self.mat.view(self.nc, self.nc).double()
+        inter = m.diag()
+        union = m.sum(0) + m.sum(1) - inter
+        valid = union > 0
+        return float((inter[valid] / union[valid]).mean()) if valid.any() else 0.0
+
+
+class LayerwiseStep:
+    """criterions = [supervised, kd, hint] as in train.py:48-50; `model` is a DepthwiseStudent."""
+
+    def __init__(self, model, criterions, optimizer, accumulation_steps=1, process_group=None, log_supervised=True):
+        self.model, self.criterions, self.optimizer = model, criterions, optimizer
+        self.accumulation_steps = int(accumulation_steps)
+        self.group = process_group
+        self.log_supervised = log_supervised
+        self.bucket = GradBucket(model.trainable_parameters())
+
+    def rebuild_bucket(self):
+        self.bucket = GradBucket(self.model.trainable_parameters())
+
+    def __call__(self, data, target, batch_idx):
+        acc = self.accumulation_steps
+        output_st, output_tc = self.model(data)
+        pairs = list(zip(self.model.student_hidden_outputs, self.model.teacher_hidden_outputs))
+        hint_loss = reduce(lambda a, st: a + self.criterions[2](st[0], st[1]), pairs, 0) / acc
+        with torch.no_grad():  # logged, never back-propagated by this trainer
+            kd_loss = self.criterions[1](output_st, output_tc) / acc
+            if self.log_supervised and target is not None:
+                supervised = self.criterions[0](output_st, target) / acc
+                teacher_loss = self.criterions[0](output_tc, target)
+            else:
+                supervised = teacher_loss = torch.zeros((), device=data.device)
+        loss = hint_loss
+        if torch.is_tensor(loss):
+            loss.backward()
+        if batch_idx % acc == 0:
+            self.bucket.all_reduce_mean(self.group)
+            self.optimizer.step()
+            self.bucket.zero()  # == optimizer.zero_grad() for the trainable set, keeps the flat views alive
+        return {"loss": loss, "hint_loss": hint_loss, "kd_loss": kd_loss, "supervised_loss": supervised,
+                "teacher_loss": teacher_loss, "output_st": output_st.detach(), "output_tc": output_tc}

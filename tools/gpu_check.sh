@@ -19,4 +19,6 @@ run nchw 600 "nchw"
 run gemm 400 "gemm or epilogue"
 run seeded 600 "seeded"
 run full_size 600 "full_size or errors"
+echo "=== student" >> gpurun_out/check.log; timeout -s KILL 300 python -m pytest tests/test_student_trainer.py -q -m gpu -p no:cacheprovider 2>&1 | tail -5 >> gpurun_out/check.log
+echo "=== smoke" >> gpurun_out/check.log; timeout -s KILL 300 python __graft_entry__.py smoke 2>&1 | tail -3 >> gpurun_out/check.log
 grep -E "^===|passed|failed|exit=|Error|error" gpurun_out/check.log | head -80
