@@ -25,12 +25,13 @@
 #include <stdlib.h>
 
 #include "dw_kernels.cuh"
+#include "dw_tc_common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace kdcc {
 
 constexpr int TC_TILE = 128;     // output rows and columns per tile (UMMA M = 128)
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 288;  // warp 0 TMA, warps 1,6,7,8 MMA issuers (N-tiles round-robin), warps 2-5 epilogue
 
 struct DwTcParams {
   int N, C, Hi, Wi, Ho, Wo, k, dil, pad, flip;
@@ -41,12 +42,14 @@ struct DwTcParams {
   int rows;       // rows per A tile: 128 (+ halo when single)
   int box_bytes;  // ceil8(rows) * 128
   int extra;      // zero columns added on the left so that the TMA column origin is 16-byte aligned
+  int issuers;    // MMA-issuing threads (1, 2 or 4)
   int ksteps;     // ceil((NT + halo) / 16)
   int tiles_h, tiles_w;
-  long items;
+  int planes, splits;  // planes per channel (N * tiles), CTAs sharing a channel
+  long pairs;          // units = C * splits
   const float *w, *bias;
   __nv_bfloat16 *out;
-  int dbg;  // KDCC_TC_DEBUG: descriptor base-offset mode for row-shifted starts (0 none, 1 phase, 2 negated phase)
+  int dbg;  // KDCC_TC_DEBUG (timing experiments only): 1 skip Toeplitz rebuild, 2 skip MMAs, 4 skip epilogue stores
 };
 
 // K-major, SWIZZLE_128B operand tile: 128-byte rows, 8-row groups 1024 B apart, tile base 1024-byte aligned;
@@ -107,12 +110,12 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(b_full(s), 128);
-      ptx::mbar_init(t_full(s), 1);
+      ptx::mbar_init(t_full(s), p.issuers);   // one commit per issuing thread
       ptx::mbar_init(t_empty(s), 4);
     }
     for (int s = 0; s < AS; ++s) {
       ptx::mbar_init(a_full(s), 1);
-      ptx::mbar_init(a_empty(s), 1);
+      ptx::mbar_init(a_empty(s), p.issuers);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tm_in);
@@ -123,11 +126,10 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode = [&](long item, int &n, int &c, int &i0, int &j0) {
-    const int tj = (int)(item % p.tiles_w); item /= p.tiles_w;
-    const int ti = (int)(item % p.tiles_h); item /= p.tiles_h;
-    c = (int)(item % p.C);
-    n = (int)(item / p.C);
+  auto decode = [&](int pl, int &n, int &i0, int &j0) {
+    const int tj = pl % p.tiles_w; pl /= p.tiles_w;
+    const int ti = pl % p.tiles_h;
+    n = pl / p.tiles_h;
     i0 = ti * TC_TILE;
     j0 = tj * TC_TILE;
   };
@@ -136,9 +138,10 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
     // ===== TMA producer: the input window of an item, once (single) or once per tap row =====
     int as = 0; uint32_t aph = 0;
     const int tiles = p.single ? 1 : p.k;
-    for (long item = blockIdx.x; item < p.items; item += gridDim.x) {
-      int n, c, i0, j0;
-      decode(item, n, c, i0, j0);
+    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next()) {
+      const int c = w.channel();
+      int n, i0, j0;
+      decode(w.pl, n, i0, j0);
       for (int u = 0; u < tiles; ++u) {
         ptx::mbar_wait(a_empty(as), aph ^ 1);
         ptx::mbar_arrive_expect_tx(a_full(as), (uint32_t)(p.nbox * p.rows * 128));
@@ -148,8 +151,10 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
         if (++as == AS) { as = 0; aph ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
+  } else if ((warp == 1 || (warp >= 6 && warp - 5 < p.issuers)) && lane == 0) {
+    // ===== MMA issuers: N-tile t belongs to issuer t % issuers (each tile has its own TMEM columns) =====
+    const int t_first = warp == 1 ? 0 : warp - 5;
+    const int t_step = p.issuers;
     // instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, N = NT, M = 128
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
     constexpr int T = TC_TILE / NT;
@@ -167,14 +172,17 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
         const int q0 = t * NT + kk * 16;  // first window column of this 16-wide reduction slice
         a_off[t][kk] = ((uint32_t)(q0 >> 6) * (uint32_t)p.box_bytes + (uint32_t)(q0 & 63) * 2u) >> 4;
       }
-    int it = 0;
+    int it = 0, unit = -1;
     int as = 0; uint32_t aph = 0;
-    for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       ptx::mbar_wait(t_empty(s), ph ^ 1);
-      ptx::mbar_wait(b_full(s), ph);
-      const uint32_t b0 = b_base + s * b_stage_bytes;
+      if (w.first_of_unit()) {  // the Toeplitz operand is per channel: one build per unit
+        ++unit;
+        ptx::mbar_wait(b_full(unit & 1), (unit >> 1) & 1);
+      }
+      const uint32_t b0 = b_base + (unit & 1) * b_stage_bytes;
       const uint32_t d0 = tmem_base + (uint32_t)(s * TC_TILE);
 #pragma unroll 1
       for (int u = 0; u < p.k; ++u) {
@@ -186,11 +194,13 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
         const uint32_t b_lo = (((b0 + (uint32_t)u * BU_BYTES) & 0x3FFFF) >> 4) | b_lbo;
         const uint32_t acc0 = u ? 1u : 0u;
 #pragma unroll
-        for (int t = 0; t < T; ++t)
+        for (int t = 0; t < T; ++t) {
+          if (t % t_step != t_first || (p.dbg & 2)) continue;
 #pragma unroll
           for (int kk = 0; kk < KS; ++kk)
             tc_mma(d0 + (uint32_t)(t * NT), a_lo + a_off[t][kk], a_hi, b_lo + (uint32_t)(kk * 2 * NT), b_hi, idesc,
                    kk ? 1u : acc0);
+        }
         if (!p.single || u == p.k - 1) {
           ptx::umma_commit(a_empty(as));  // tile free once these MMAs have read it
           if (++as == AS) { as = 0; aph ^= 1; }
@@ -198,7 +208,7 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
       }
       ptx::umma_commit(t_full(s));
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp <= 5) {
     // ===== Toeplitz builder + epilogue (128 threads) =====
     const int et = threadIdx.x - 64;  // 0..127
     const int quad = warp & 3;
@@ -207,35 +217,40 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
       *reinterpret_cast<uint4 *>(smem_gen + (b_base - smem_base) + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
-    auto build_b = [&](long item, int s) {
-      int n, c, i0, j0;
-      decode(item, n, c, i0, j0);
+    auto build_b = [&](int c, int s) {
       const float *wc = p.w + (long)c * p.k * p.k;
       uint8_t *bs = smem_gen + (b_base - smem_base) + (size_t)s * b_stage_bytes;
-      const int band = p.k * NT * p.k;
-      for (int e = et; e < band; e += 128) {
-        const int v = e % p.k;
-        const int j = (e / p.k) % NT;
-        const int u = e / (p.k * NT);
-        const int jp = j + v * p.dil + p.extra;  // reduction column that feeds output column j through tap v
-        const float wv = __ldg(wc + (p.flip ? (p.k - 1 - u) * p.k + (p.k - 1 - v) : u * p.k + v));
-        const int off = u * BU_BYTES + (jp >> 3) * (NT * 16) + j * 16 + (jp & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(bs + off) = __float2bfloat16_rn(wv);
+      // (tap row u, output column j) pairs; the k taps of a pair land on the band j' = j + v*dil + extra
+      for (int idx = et; idx < ((p.dbg & 1) ? 0 : p.k * NT); idx += 128) {
+        const int u = idx / NT, j = idx % NT;
+        const float *wr = wc + (p.flip ? (p.k - 1 - u) * p.k : u * p.k);
+        uint8_t *row = bs + u * BU_BYTES + j * 16;
+        for (int v = 0; v < p.k; ++v) {
+          const int jp = j + v * p.dil + p.extra;
+          const float wv = __ldg(wr + (p.flip ? p.k - 1 - v : v));
+          *reinterpret_cast<__nv_bfloat16 *>(row + (jp >> 3) * (NT * 16) + (jp & 7) * 2) = __float2bfloat16_rn(wv);
+        }
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(b_full(s));
     };
 
-    if ((long)blockIdx.x < p.items) build_b(blockIdx.x, 0);
-    int it = 0;
-    for (long item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+    PlaneWalk cur(p.pairs, p.planes, p.splits, p.C), ahead(p.pairs, p.planes, p.splits, p.C);
+    if (ahead.valid()) ahead.next_unit();
+    if (cur.valid()) build_b(cur.channel(), 0);
+    int it = 0, unit = -1;
+    for (; cur.valid(); cur.next(), ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      const long next = item + gridDim.x;
-      // stage s^1 was last read by the MMAs of item it-1, whose completion we observed through t_full
-      if (next < p.items) build_b(next, s ^ 1);
-      int n, c, i0, j0;
-      decode(item, n, c, i0, j0);
+      if (cur.first_of_unit()) {
+        ++unit;
+        // build the NEXT unit's operand now: its buffer was last read by the MMAs of unit-1, all of which we
+        // observed complete (t_full of that unit's last plane) before getting here
+        if (ahead.valid()) { build_b(ahead.channel(), (unit + 1) & 1); ahead.next_unit(); }
+      }
+      const int c = cur.channel();
+      int n, i0, j0;
+      decode(cur.pl, n, i0, j0);
       ptx::mbar_wait(t_full(s), ph);
       ptx::tcgen05_fence_after();
       const int gi = i0 + quad * 32 + lane;
@@ -247,7 +262,7 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
         uint32_t vr[32];
         ptx::tmem_ld_32x32b_x32(t_row + ch * 32, vr);
         ptx::tmem_ld_wait();
-        if (gi < p.Ho) {
+        if (gi < p.Ho && !(p.dbg & 4)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = j0 + ch * 32 + q * 8;
@@ -313,7 +328,7 @@ static int tc_conv_launch(const void *in, const DwTcParams &p0, cudaStream_t st)
     if (e != cudaSuccess) return (int)e;
     attr_smem = smem;
   }
-  const int grid = (int)min(p.items, (long)kNumSMs);
+  const int grid = (int)min(p.pairs, (long)kNumSMs);
   dw_tc_conv_kernel<NT, KS><<<grid, TC_THREADS, smem, st>>>(tm, p);
   return launch_status();
 }
@@ -336,13 +351,18 @@ int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int
   p.halo = dil * (k - 1);
   p.tiles_h = ceil_div(Ho, TC_TILE);
   p.tiles_w = ceil_div(Wo, TC_TILE);
-  p.items = (long)N * C * p.tiles_h * p.tiles_w;
+  p.planes = N * p.tiles_h * p.tiles_w;
+  p.splits = tc_unit_splits(C, p.planes);
+  p.pairs = (long)C * p.splits;
   p.w = w; p.bias = bias;
   p.out = static_cast<__nv_bfloat16 *>(out);
-  if (p.items == 0) return KDCC_OK;
+  if (p.planes == 0 || C == 0) return KDCC_OK;
   const char *dbg = getenv("KDCC_TC_DEBUG");
   p.dbg = dbg ? atoi(dbg) : 0;
   p.extra = tc_extra(pad);
+  const char *is = getenv("KDCC_DW_TC_ISSUERS");
+  p.issuers = is ? max(1, min(4, atoi(is))) : 4;
+  if (p.issuers == 3) p.issuers = 2;
   const char *sg = getenv("KDCC_DW_TC_SINGLE");
   p.single = sg ? atoi(sg) : 1;
   if (TC_TILE + p.halo > 256) p.single = 0;  // TMA box rows

@@ -6,9 +6,12 @@
 // (i0 - p, j0 - p) and zero outside the image:
 //     P_u[j][q] = sum_i dy[i][j] * xw[i + u*d][q]           (a 128 x (128+halo) matrix, reduction over rows)
 //     dw[u][v] += sum_j P_u[j][j + v*d]                      (k diagonals of P_u)
-// P_u is one tcgen05.mma chain per tap row u: A = dy^T and B = xw[u*d ...] are both "MN-major" views of
-// 128B-swizzled tiles TMA landed (no transposes); the tap-row shift u*d is a +128*u*d byte bump of the
-// B descriptor start address into the one (128+halo)-row window TMA landed for the plane.
+// P_u is one tcgen05.mma chain per tap row u.  B = xw[u*d ...] is an "MN-major" view of the 128B-swizzled
+// window TMA landed once per plane (no transpose; the tap-row shift u*d is a +128*u*d byte bump of the
+// descriptor start address).  A = dy^T is the same for all k tap rows, so the epilogue warps transpose
+// the landed dy tile ONCE per plane into tensor memory (lane = dy column, 64 columns of bf16 pairs) and
+// the MMAs take A from TMEM: the shared-memory operand feed -- the limiter of these small MMAs -- then
+// only carries B.
 // (KDCC_DW_TC_SINGLE=0: conservative variant, one aligned 128-row x tile per tap row.)
 // Only k of the 128+halo columns of each P_u row are needed, so the FFMA-bound CUDA-core formulation
 // (dw_tma.cu: ~14 TFMA/s) is replaced by ~5 % efficient but 50x faster tensor-core work.
@@ -20,12 +23,13 @@
 #include <stdlib.h>
 
 #include "dw_kernels.cuh"
+#include "dw_tc_common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace kdcc {
 
 constexpr int WG_TILE = 128;
-constexpr int WG_THREADS = 192;
+constexpr int WG_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9: epilogue groups for TMEM accumulator 0 / 1
 constexpr int WG_SCR_PITCH = 36;  // floats per scratch row: 16-byte aligned rows, conflict-free 128-bit stores
 
 struct DwTcWgradParams {
@@ -38,6 +42,7 @@ struct DwTcWgradParams {
   int splits;                       // CTAs sharing one channel
   long pairs;                       // C * splits
   float *out;                       // [splits][C][k*k] (or dw itself when splits == 1)
+  int dbg;                          // KDCC_TC_DEBUG (timing experiments only): 1 skip diagonal extraction, 2 skip MMAs, 4 skip transposition
 };
 
 // MN-major SWIZZLE_128B operands: 64-element groups LBO bytes apart, 8-row (reduction) groups 1024 B apart.
@@ -60,6 +65,37 @@ __device__ __forceinline__ void wg_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t 
 
 constexpr int WG_BOX = WG_TILE * 128;  // 128 rows x 64 columns, swizzled
 
+// TMEM map (512 columns allocated): P_u accumulators at columns [0,192) and [256,448) (nq <= 192), the
+// transposed dy operand (128 reduction rows packed as 64 columns of bf16 pairs) at [192,256) and [448,512).
+constexpr uint32_t WG_TMEM_D1 = 256, WG_TMEM_A0 = 192, WG_TMEM_A1 = 448;
+
+// A from TMEM, B from shared memory
+__device__ __forceinline__ void wg_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
 template <int K>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
@@ -69,25 +105,28 @@ dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const int x_bytes = p.nbox * p.box_bytes;
   const int XS = p.x_stages;
-  const uint32_t dy_base = smem_base + XS * x_bytes;
-  const uint32_t scr_off = XS * x_bytes + 4 * WG_BOX;
-  const uint32_t bar_base = smem_base + scr_off + 4 * 32 * WG_SCR_PITCH * 4;
+  const uint32_t dy_off = XS * x_bytes;                     // one stage = 2 boxes of dy (consumed at once by the transposers)
+  const uint32_t scr_off = dy_off + 2 * WG_BOX;
+  const uint32_t bar_off = scr_off + 8 * 32 * WG_SCR_PITCH * 4;
+  const uint32_t bar_base = smem_base + bar_off;
   auto dy_full = [&](int s) { return bar_base + 8u * s; };
   auto dy_empty = [&](int s) { return bar_base + 8u * (2 + s); };
   auto t_full = [&](int s) { return bar_base + 8u * (4 + s); };
   auto t_empty = [&](int s) { return bar_base + 8u * (6 + s); };
-  auto x_full = [&](int s) { return bar_base + 8u * (8 + s); };
-  auto x_empty = [&](int s) { return bar_base + 8u * (12 + s); };  // up to 4 x stages
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_gen + (bar_base - smem_base) + 128);
-  float *red = reinterpret_cast<float *>(smem_gen + (bar_base - smem_base) + 192);  // [4][K*K]
+  auto a_full = [&](int s) { return bar_base + 8u * (8 + s); };   // dy^T of a plane is in TMEM
+  auto x_full = [&](int s) { return bar_base + 8u * (10 + s); };
+  auto x_empty = [&](int s) { return bar_base + 8u * (14 + s); };  // up to 4 x stages
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_gen + bar_off + 160);
+  float *red = reinterpret_cast<float *>(smem_gen + bar_off + 192);  // [8 warps][K*K]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(dy_full(s), 1);
-      ptx::mbar_init(dy_empty(s), 1);
+      ptx::mbar_init(dy_empty(s), 8);
       ptx::mbar_init(t_full(s), 1);
       ptx::mbar_init(t_empty(s), 4);
+      ptx::mbar_init(a_full(s), 8);
     }
     for (int s = 0; s < XS; ++s) {
       ptx::mbar_init(x_full(s), 1);
@@ -112,123 +151,158 @@ dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   };
 
   if (warp == 0 && lane == 0) {
-    // ===== TMA producer: dy tile once per plane, one x tile per tap row =====
+    // ===== TMA producer: dy tile once per plane, the x window once per plane (or one tile per tap row) =====
     int it = 0;
     int xs = 0; uint32_t xph = 0;
-    for (long pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-      const int c = (int)(pair % p.C), split = (int)(pair / p.C);
-      for (int pl = split; pl < p.planes; pl += p.splits, ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        int n, i0, j0;
-        decode_plane(pl, n, i0, j0);
-        ptx::mbar_wait(dy_empty(s), ph ^ 1);
-        ptx::mbar_arrive_expect_tx(dy_full(s), 2 * WG_BOX);
-        for (int b = 0; b < 2; ++b)
-          ptx::tma_load_4d(dy_base + (2 * s + b) * WG_BOX, &tm_dy, dy_full(s), j0 + 64 * b, i0, c, n);
-        for (int u = 0; u < (p.single ? 1 : K); ++u) {
-          ptx::mbar_wait(x_empty(xs), xph ^ 1);
-          ptx::mbar_arrive_expect_tx(x_full(xs), (uint32_t)(p.nbox * p.rows * 128));
-          for (int b = 0; b < p.nbox; ++b)
-            ptx::tma_load_4d(smem_base + xs * x_bytes + b * p.box_bytes, &tm_x, x_full(xs),
-                             j0 - p.pad - p.extra + 64 * b, i0 - p.pad + u * p.dil, c, n);
+    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int c = w.channel();
+      int n, i0, j0;
+      decode_plane(w.pl, n, i0, j0);
+      ptx::mbar_wait(dy_empty(0), (uint32_t)(it & 1) ^ 1);
+      ptx::mbar_arrive_expect_tx(dy_full(0), 2 * WG_BOX);
+      for (int b = 0; b < 2; ++b)
+        ptx::tma_load_4d(smem_base + dy_off + b * WG_BOX, &tm_dy, dy_full(0), j0 + 64 * b, i0, c, n);
+      for (int u = 0; u < (p.single ? 1 : K); ++u) {
+        ptx::mbar_wait(x_empty(xs), xph ^ 1);
+        ptx::mbar_arrive_expect_tx(x_full(xs), (uint32_t)(p.nbox * p.rows * 128));
+        for (int b = 0; b < p.nbox; ++b)
+          ptx::tma_load_4d(smem_base + xs * x_bytes + b * p.box_bytes, &tm_x, x_full(xs),
+                           j0 - p.pad - p.extra + 64 * b, i0 - p.pad + u * p.dil, c, n);
+        if (++xs == XS) { xs = 0; xph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer: P_u (128 dy columns x nq window columns) = dy^T [TMEM] * x_u [smem, MN-major] =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) |
+                           ((uint32_t)(p.nq >> 3) << 17) | ((uint32_t)(WG_TILE >> 4) << 24);
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
+    int it = 0, tit = 0;
+    int xs = 0; uint32_t xph = 0;
+    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      ptx::mbar_wait(a_full(s), ph);
+      const uint32_t a_tmem = tmem_base + (s ? WG_TMEM_A1 : WG_TMEM_A0);
+      for (int u = 0; u < K; ++u, ++tit) {
+        const int tb = tit & 1;
+        if (!p.single || u == 0) ptx::mbar_wait(x_full(xs), xph);
+        ptx::mbar_wait(t_empty(tb), ((tit >> 1) & 1) ^ 1);
+        ptx::tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (tb ? WG_TMEM_D1 : 0u);
+        // single window: tap row u starts u*dil rows (128 B each) further down the same tile
+        const uint32_t xa = smem_base + xs * x_bytes + (p.single ? (uint32_t)(u * p.dil) * 128u : 0u);
+        const uint32_t b_lo = ((xa & 0x3FFFF) >> 4) | ((uint32_t)(p.box_bytes >> 4) << 16);
+        if (!(p.dbg & 2)) {
+#pragma unroll
+          for (int ks = 0; ks < WG_TILE / 16; ++ks)  // 16 reduction rows per MMA: 8 TMEM columns of A, 2 KB of B
+            wg_mma_ts(d_tmem, a_tmem + ks * 8, b_lo + ks * 128, b_hi, idesc, ks ? 1u : 0u);
+        }
+        ptx::umma_commit(t_full(tb));
+        if (!p.single || u == K - 1) {
+          ptx::umma_commit(x_empty(xs));
           if (++xs == XS) { xs = 0; xph ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer: P_u = dy^T (128 cols x 128 rows) * x_u (128 rows x nq cols) =====
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(p.nq >> 3) << 17) | ((uint32_t)(WG_TILE >> 4) << 24);
-    int it = 0, tit = 0;
-    int xs = 0; uint32_t xph = 0;
-    for (long pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-      const int split = (int)(pair / p.C);
-      for (int pl = split; pl < p.planes; pl += p.splits, ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        ptx::mbar_wait(dy_full(s), ph);
-        const uint32_t dys = dy_base + 2 * s * WG_BOX;
-        for (int u = 0; u < K; ++u, ++tit) {
-          const int tb = tit & 1;
-          if (!p.single || u == 0) ptx::mbar_wait(x_full(xs), xph);
-          ptx::mbar_wait(t_empty(tb), ((tit >> 1) & 1) ^ 1);
-          ptx::tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(tb * 256);
-          // single window: tap row u starts u*dil rows (128 B each) further down the same tile
-          const uint32_t xa = smem_base + xs * x_bytes + (p.single ? (uint32_t)(u * p.dil) * 128u : 0u);
-          // lo halves: start address | LBO; hi half (shared): SBO 1024, version 1, SWIZZLE_128B
-          const uint32_t a_lo = ((dys & 0x3FFFF) >> 4) | ((uint32_t)(WG_BOX >> 4) << 16);
-          const uint32_t b_lo = ((xa & 0x3FFFF) >> 4) | ((uint32_t)(p.box_bytes >> 4) << 16);
-          const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-#pragma unroll
-          for (int ks = 0; ks < WG_TILE / 16; ++ks)  // 16 reduction rows per MMA = 2 KB (128 x 16-byte units) in both tiles
-            wg_mma(d_tmem, a_lo + ks * 128, b_lo + ks * 128, hi, idesc, ks ? 1u : 0u);
-          ptx::umma_commit(t_full(tb));
-          if (!p.single || u == K - 1) {
-            ptx::umma_commit(x_empty(xs));
-            if (++xs == XS) { xs = 0; xph ^= 1; }
-          }
-        }
-        ptx::umma_commit(dy_empty(s));
-      }
-    }
   } else if (warp >= 2) {
-    // ===== epilogue: diagonals of P_u -> k*k register partial sums =====
+    // ===== operand transposer + epilogue (128 threads; thread = dy column j = TMEM lane) =====
     const int quad = warp & 3;
-    float *scr = reinterpret_cast<float *>(smem_gen + scr_off) + (quad * 32 + lane) * WG_SCR_PITCH;
+    const int grp = (warp - 2) >> 2;  // 0: TMEM accumulator 0 and dy rows 0-63, 1: accumulator 1 and dy rows 64-127
+    const int j = quad * 32 + lane;
+    float *scr = reinterpret_cast<float *>(smem_gen + scr_off) + (grp * 128 + j) * WG_SCR_PITCH;
     const int nch = (31 + p.halo + p.extra) / 32 + 1;  // 32-column chunks a warp's rows reach into
-    int tit = 0;
-    for (long pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-      const int c = (int)(pair % p.C), split = (int)(pair / p.C);
-      float acc[K][K];
+
+    // dy tile (two 128B-swizzled boxes of 64 columns) -> TMEM lane j, column r/2 = (dy[r][j], dy[r+1][j])
+    auto transpose_dy = [&](int it) {
+      const int s = it & 1;
+      ptx::mbar_wait(dy_full(0), (uint32_t)(it & 1));
+      const uint8_t *tile = smem_gen + dy_off + (size_t)(j >> 6) * WG_BOX;
+      const int chunk = (j & 63) >> 3, within = (j & 7) * 2;
+      const uint32_t t_dst = tmem_base + (s ? WG_TMEM_A1 : WG_TMEM_A0) + ((uint32_t)(quad * 32) << 16);
+      {
+        const int half = grp;  // each group packs 64 reduction rows = 32 TMEM columns
+        uint32_t regs[32];
 #pragma unroll
-      for (int u = 0; u < K; ++u)
+        for (int q = 0; q < 32; ++q) {
+          const int r = half * 64 + 2 * q;  // rows r (even) and r + 1 share the 8-row swizzle phase pair (r & 7, r & 7 + 1)
+          const uint32_t lo = *reinterpret_cast<const uint16_t *>(tile + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+          const uint32_t hi = *reinterpret_cast<const uint16_t *>(tile + (r + 1) * 128 + ((chunk ^ ((r + 1) & 7)) << 4) + within);
+          regs[q] = lo | (hi << 16);
+        }
+        tmem_st_32x32b_x32(t_dst + half * 32, regs);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(a_full(s));    // operand ready for the MMA thread
+        ptx::mbar_arrive(dy_empty(0));  // the smem tile can be refilled
+      }
+    };
+
+    int it = 0, tit = 0;
+    PlaneWalk cur(p.pairs, p.planes, p.splits, p.C), nxt(p.pairs, p.planes, p.splits, p.C);
+    if (nxt.valid()) nxt.next();
+    if (cur.valid()) transpose_dy(0);
+    float acc[K][K];
+    for (; cur.valid(); ++it) {
+      // the other TMEM A buffer was last read by the MMAs of plane it-1, all observed complete through t_full
+      if (nxt.valid()) transpose_dy(it + 1);
+      if (cur.first_of_unit()) {
 #pragma unroll
-        for (int v = 0; v < K; ++v) acc[u][v] = 0.f;
-      for (int pl = split; pl < p.planes; pl += p.splits) {
+        for (int u = 0; u < K; ++u)
 #pragma unroll
-        for (int u = 0; u < K; ++u, ++tit) {
-          const int tb = tit & 1;
-          ptx::mbar_wait(t_full(tb), (tit >> 1) & 1);
-          ptx::tcgen05_fence_after();
-          const uint32_t t_row = tmem_base + (uint32_t)(tb * 256) + ((uint32_t)(quad * 32) << 16);
-          for (int c3 = 0; c3 < nch; ++c3) {
-            const int col0 = 32 * (quad + c3);
-            if (col0 >= p.nq) break;
-            uint32_t vr[32];
-            ptx::tmem_ld_32x32b_x32(t_row + col0, vr);
-            ptx::tmem_ld_wait();
+          for (int v = 0; v < K; ++v) acc[u][v] = 0.f;
+      }
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<uint4 *>(scr + 4 * q) = make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
+      for (int u = 0; u < K; ++u, ++tit) {
+        const int tb = tit & 1;
+        if (tb != grp) continue;  // the other group drains this accumulator
+        ptx::mbar_wait(t_full(tb), (tit >> 1) & 1);
+        ptx::tcgen05_fence_after();
+        const uint32_t t_row = tmem_base + (tb ? WG_TMEM_D1 : 0u) + ((uint32_t)(quad * 32) << 16);
+        for (int c3 = 0; c3 < ((p.dbg & 1) ? 0 : nch); ++c3) {
+          const int col0 = 32 * (quad + c3);
+          if (col0 >= p.nq) break;
+          uint32_t vr[32];
+          ptx::tmem_ld_32x32b_x32(t_row + col0, vr);
+          ptx::tmem_ld_wait();
 #pragma unroll
-            for (int v = 0; v < K; ++v) {
-              const int e = lane + v * p.dil + p.extra - 32 * c3;  // window column of tap v for row j, relative to this chunk
-              if (e >= 0 && e < 32) acc[u][v] += scr[e];
-            }
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4 *>(scr + 4 * q) = make_uint4(vr[4 * q], vr[4 * q + 1], vr[4 * q + 2], vr[4 * q + 3]);
+#pragma unroll
+          for (int v = 0; v < K; ++v) {
+            const int e = lane + v * p.dil + p.extra - 32 * c3;  // window column of tap v for row j, relative to this chunk
+            if (e >= 0 && e < 32) acc[u][v] += scr[e];
           }
-          ptx::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(t_empty(tb));
         }
+        ptx::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(t_empty(tb));
       }
-      // channel (pair) finished: sum the 128 rows -- shuffle inside the warp, fixed order across warps
+      if (cur.last_of_unit()) {
+        // channel (pair) finished: sum the 128 rows -- shuffle inside the warp, fixed order across warps
 #pragma unroll
-      for (int u = 0; u < K; ++u)
+        for (int u = 0; u < K; ++u)
 #pragma unroll
-        for (int v = 0; v < K; ++v) {
-          const float r = warp_sum(acc[u][v]);
-          if (lane == 0) red[quad * K * K + u * K + v] = r;
+          for (int v = 0; v < K; ++v) {
+            const float r = warp_sum(acc[u][v]);
+            if (lane == 0) red[(grp * 4 + quad) * K * K + u * K + v] = r;
+          }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int et = threadIdx.x - 64;
+        if (et < K * K) {
+          float sum = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sum += red[q * K * K + et];  // fixed order: group, then quadrant
+          p.out[((long)cur.split() * p.C + cur.channel()) * (K * K) + et] = sum;
         }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = threadIdx.x - 64;
-      if (et < K * K) {
-        // warps 2,3,4,5 own quadrants 2,3,0,1: add in quadrant order 0..3 for a fixed summation order
-        const float sum = ((red[0 * K * K + et] + red[1 * K * K + et]) + red[2 * K * K + et]) + red[3 * K * K + et];
-        p.out[((long)split * p.C + c) * (K * K) + et] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      cur.next();
+      if (nxt.valid()) nxt.next();
     }
   }
 
@@ -246,16 +320,7 @@ __global__ void dw_tc_wgrad_reduce_kernel(const float *__restrict__ part, float 
   dw[i] = acc;
 }
 
-static int wg_splits(int C, int planes) {
-  int best = 1;
-  long best_cost = -1;
-  for (int s = 1; s <= planes && s <= 16; ++s) {
-    const long rounds = ceil_div<long>((long)C * s, kNumSMs);
-    const long cost = rounds * ceil_div(planes, s) * 16 + rounds;  // planes per CTA dominate; small per-pair overhead
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
-  }
-  return best;
-}
+static int wg_splits(int C, int planes) { return tc_unit_splits(C, planes); }
 
 size_t dw_tc_wgrad_workspace(int N, int C, int Ho, int Wo, int k) {
   const int planes = N * ceil_div(Ho, WG_TILE) * ceil_div(Wo, WG_TILE);
@@ -281,7 +346,7 @@ static int wgrad_launch(const void *x, const void *dy, float *dw, float *part, c
     if (rc) return rc;
   }
   p.out = p.splits == 1 ? dw : part;
-  const int fixed = 4 * WG_BOX + 4 * 32 * WG_SCR_PITCH * 4 + 192 + 4 * K * K * 4 + 64 + 1024;
+  const int fixed = 2 * WG_BOX + 8 * 32 * WG_SCR_PITCH * 4 + 192 + 8 * K * K * 4 + 64 + 1024;  // dy, scratch, barriers, red, slack
   p.x_stages = min(p.single ? 2 : 4, (220 * 1024 - fixed) / (p.nbox * p.box_bytes));
   if (p.x_stages < 2) return KDCC_ESHAPE;
   const int smem = p.x_stages * p.nbox * p.box_bytes + fixed;
@@ -305,6 +370,8 @@ int dw_tc_wgrad(const void *x, const void *dy, float *dw, float *part, int N, in
   DwTcWgradParams p{};
   p.N = N; p.C = C; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.k = k; p.dil = dil; p.pad = pad;
   p.halo = dil * (k - 1);
+  const char *dbg = getenv("KDCC_TC_DEBUG");
+  p.dbg = dbg ? atoi(dbg) : 0;
   p.extra = (8 - pad % 8) % 8;
   p.nq = (WG_TILE + p.halo + p.extra + 15) / 16 * 16;
   p.nbox = ceil_div(p.nq, 64);
@@ -318,7 +385,7 @@ int dw_tc_wgrad(const void *x, const void *dy, float *dw, float *part, int N, in
   p.planes = N * p.tiles_h * p.tiles_w;
   p.splits = wg_splits(C, p.planes);
   p.pairs = (long)C * p.splits;
-  if (p.nq > 256) return KDCC_ESHAPE;
+  if (p.nq > 192) return KDCC_ESHAPE;  // TMEM map: two P_u buffers of <= 192 columns + two dy^T operands of 64
   switch (k) {
     case 1: return wgrad_launch<1>(x, dy, dw, part, p, st);
     case 3: return wgrad_launch<3>(x, dy, dw, part, p, st);
