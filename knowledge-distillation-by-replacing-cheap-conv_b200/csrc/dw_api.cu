@@ -53,7 +53,10 @@ KDCC_API size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, i
                                             int dtype) {
   int Ho, Wo;
   if (check_geometry(N, H, W, C, k, dil, pad, layout, dtype, &Ho, &Wo) || N == 0) return 0;
-  if (layout == KDCC_LAYOUT_NCHW) return dw_tc_wgrad_workspace(N, C, Ho, Wo, k);
+  if (layout == KDCC_LAYOUT_NCHW) {
+    const size_t a = dw_tc_wgrad_workspace(N, C, Ho, Wo, k), b = dw_tc_wgrad2_workspace(N, C, k);
+    return a > b ? a : b;
+  }
   const int vn = dtype == KDCC_F32 ? 4 : 8;
   size_t splits = (size_t)dw_direct_wgrad_splits(N, Ho, C, k, vn);
   if (dtype == KDCC_BF16 && dw_tma_supported(C, k, dil)) {
@@ -84,7 +87,11 @@ KDCC_API int kdcc_dw_bwd(const void *x, const float *w, const void *dy, void *dx
       rc = dw_tc_conv(dy, w, nullptr, dx, N, C, Ho, Wo, H, W, k, dil, padt, 1, st);
       if (rc) return rc;
     }
-    if (dw) return dw_tc_wgrad(x, dy, dw, static_cast<float *>(workspace), N, C, H, W, Ho, Wo, k, dil, pad, st);
+    if (dw) {
+      if (dw_tc_wgrad2_supported(H, W, Ho, Wo, k, dil, pad))
+        return dw_tc_wgrad2(x, dy, dw, static_cast<float *>(workspace), N, C, H, W, k, dil, pad, st);
+      return dw_tc_wgrad(x, dy, dw, static_cast<float *>(workspace), N, C, H, W, Ho, Wo, k, dil, pad, st);
+    }
     return KDCC_OK;
   }
   const bool tma = use_tma(C, k, dil, dtype);

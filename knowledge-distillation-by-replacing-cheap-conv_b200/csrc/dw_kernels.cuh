@@ -33,5 +33,10 @@ int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int
 int dw_tc_wgrad(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, int Ho, int Wo,
                 int k, int dil, int pad, cudaStream_t st);
 size_t dw_tc_wgrad_workspace(int N, int C, int Ho, int Wo, int k);
+// whole-plane variant (H, W <= 128, same-size convolution): dw_tc_wgrad2.cu
+bool dw_tc_wgrad2_supported(int H, int W, int Ho, int Wo, int k, int dil, int pad);
+int dw_tc_wgrad2(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, int k, int dil,
+                 int pad, cudaStream_t st);
+size_t dw_tc_wgrad2_workspace(int N, int C, int k);
 
 }  // namespace kdcc
