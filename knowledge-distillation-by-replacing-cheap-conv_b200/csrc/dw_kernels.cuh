@@ -33,6 +33,10 @@ int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int
 int dw_tc_wgrad(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, int Ho, int Wo,
                 int k, int dil, int pad, cudaStream_t st);
 size_t dw_tc_wgrad_workspace(int N, int C, int Ho, int Wo, int k);
+// whole-plane, column-phase variant of the convolution (H, W <= 128, same-size, pad % dil == 0): dw_tc2.cu
+bool dw_tc_conv2_supported(int Hi, int Wi, int Ho, int Wo, int k, int dil, int pad);
+int dw_tc_conv2(const void *in, const float *w, const float *bias, void *out, int N, int C, int H, int W, int k, int dil,
+                int pad, int flip, cudaStream_t st);
 // whole-plane variant (H, W <= 128, same-size convolution): dw_tc_wgrad2.cu
 bool dw_tc_wgrad2_supported(int H, int W, int Ho, int Wo, int k, int dil, int pad);
 int dw_tc_wgrad2(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, int k, int dil,

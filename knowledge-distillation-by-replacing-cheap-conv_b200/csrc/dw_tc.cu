@@ -346,6 +346,7 @@ static int tc_conv_dispatch_ks(const void *in, const DwTcParams &p, cudaStream_t
 
 int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int N, int C, int Hi, int Wi, int Ho,
                int Wo, int k, int dil, int pad, int flip, cudaStream_t st) {
+  if (dw_tc_conv2_supported(Hi, Wi, Ho, Wo, k, dil, pad)) return dw_tc_conv2(in, w, bias, out, N, C, Hi, Wi, k, dil, pad, flip, st);
   DwTcParams p{};
   p.N = N; p.C = C; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo; p.k = k; p.dil = dil; p.pad = pad; p.flip = flip;
   p.halo = dil * (k - 1);

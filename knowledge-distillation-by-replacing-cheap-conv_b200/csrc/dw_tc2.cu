@@ -1,0 +1,346 @@
+// Depthwise k x k convolution on the tensor cores, whole-plane / column-phase variant (bf16, NCHW planes,
+// H, W <= 128, same-size convolution, pad % dil == 0).
+//
+// dw_tc.cu multiplies the 128-row image window by a banded Toeplitz matrix whose band, for a dilated tap set,
+// is mostly zeros: with d = 5 only every fifth input column of a 72-column reduction slice meets a tap.  Here the
+// columns are first regrouped by their residue b = j mod d ("phase").  Inside one phase the dilated row filter is
+// a DENSE k-tap filter over q = j div d, so per phase b and tap row u
+//         out_b[i][q] += sum_{q'} X_b[i + u*d - p][q'] * T_u[q'][q],      T_u[q'][q] = w[u][q' - q + p/d]
+// is one 128 x 32 x 32 product (two K=16 tcgen05.mma): 2*d*k = 90 MMAs per plane instead of 180, and every
+// plane is read from shared memory 9 instead of ~11 times.  tools/mma_probe.cu: these SS MMAs cost 43 + N/2 = 59
+// clocks each whatever the layout, so the plane costs ~5.3 kclk -- the kernel is tensor-issue bound, not HBM bound.
+//  * TMA lands the bare plane (no halo) as two 128B-swizzled 64-column boxes.
+//  * Four warps regroup it into the phase-major operand X_b: [phase][16-byte K chunk][row][8 phase-columns], an
+//    un-swizzled K-major layout whose rows are 16 bytes apart, so the tap-row shift u*d is a +16*u*d byte bump of the
+//    descriptor start address.  The pad rows above / below the plane are zeros written once; pad columns do not
+//    exist at all (T_u simply has no entry for them).  X_b is double buffered.
+//  * The same warps rebuild the k Toeplitz tiles (32 x 32 bf16 each) once per channel.
+//  * D = d accumulators of 128 x 32 fp32 in TMEM, double buffered; four epilogue warps re-interleave the phases in
+//    registers (thread = output row) and store bf16 rows.
+// The input-gradient form is the same kernel over dy with mirrored taps.
+// Reference semantics: models/students/transform_blocks/depthwise_separable_conv.py:7-8,12 (+ autograd).
+#include <stdlib.h>
+
+#include "dw_kernels.cuh"
+#include "dw_tc_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace kdcc {
+
+constexpr int C2_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 regroup + Toeplitz, warps 6-9 epilogue
+constexpr int C2_STG = 2 * 128 * 128;  // one landed plane: two boxes of 128 rows x 128 bytes
+constexpr int C2_TZ = 2048;            // one Toeplitz tile: [4 K chunks][32 columns][16 bytes]
+constexpr int C2_MAXROWS = 128 + 48;   // operand rows: plane + halo
+
+struct C2Params {
+  int N, C, H, W, k, dil, pad, flip;
+  int rows_p;     // 128 + dil*(k-1): rows of the phase-major operand
+  int ks;         // K slices of 16 phase-columns in use (1 or 2)
+  int qoff;       // pad / dil
+  int planes, splits;
+  long pairs;
+  const float *w, *bias;
+  __nv_bfloat16 *out;
+  int dbg;  // KDCC_TC_DEBUG (timing experiments only): 1 skip Toeplitz rebuild, 2 skip MMAs, 4 skip stores, 8 skip regrouping
+};
+
+template <int D>
+__global__ void __launch_bounds__(C2_THREADS, 1)
+dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const C2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const uint32_t lbo = (uint32_t)p.rows_p * 16u;       // bytes between K chunks of the operand
+  const uint32_t xp_bytes = (uint32_t)D * 4u * lbo;    // one operand buffer
+  const uint32_t xp_off = 2 * C2_STG;
+  const uint32_t tz_off = xp_off + 2 * xp_bytes;
+  const uint32_t tz_bytes = (uint32_t)p.k * C2_TZ;
+  constexpr uint32_t OB = 32 * 16 * D;                 // one epilogue staging tile: 32 rows x 8*D bf16 columns
+  const uint32_t ob_off = (tz_off + 2 * tz_bytes + 127u) & ~127u;
+  const uint32_t bar_off = ob_off + 4 * 2 * OB;
+  const uint32_t bar_base = smem_base + bar_off;
+  auto stg_full = [&](int s) { return bar_base + 8u * s; };
+  auto stg_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto xp_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto xp_empty = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto t_full = [&](int s) { return bar_base + 8u * (10 + s); };
+  auto t_empty = [&](int s) { return bar_base + 8u * (12 + s); };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_gen + bar_off + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // operand buffers and Toeplitz tiles start as zeros: pad rows, unused phase-columns and everything off the band
+  // are never written again
+  for (uint32_t i = threadIdx.x; i < (ob_off - xp_off) / 16; i += C2_THREADS)
+    reinterpret_cast<uint4 *>(smem_gen + xp_off)[i] = make_uint4(0, 0, 0, 0);
+  ptx::fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(stg_full(s), 1);
+      ptx::mbar_init(stg_empty(s), 4);
+      ptx::mbar_init(xp_full(s), 4);
+      ptx::mbar_init(xp_empty(s), 1);
+      ptx::mbar_init(b_full(s), 4);
+      ptx::mbar_init(t_full(s), 1);
+      ptx::mbar_init(t_empty(s), 4);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tm_in);
+    ptx::prefetch_tensormap(&tm_out);
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)));
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // ===== TMA producer: one bare plane per item =====
+      int it = 0;
+      for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+        const int s = it & 1;
+        ptx::mbar_wait(stg_empty(s), ((it >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(stg_full(s), C2_STG);
+        for (int b = 0; b < 2; ++b)
+          ptx::tma_load_4d(smem_base + s * C2_STG + b * (C2_STG / 2), &tm_in, stg_full(s), 64 * b, 0, w.channel(), w.pl);
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // ===== MMA issuer: D_b (128 rows x 32 phase-columns) += X_b[u*d ...] (128 x 16) * T_u (16 x 32) =====
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t hi = (128u >> 4) | (1u << 14);  // 8-row groups 128 B apart, descriptor version 1, no swizzle
+      const uint32_t a_lbo = (lbo >> 4) << 16;
+      constexpr uint32_t b_lbo = (512u >> 4) << 16;      // Toeplitz K chunks: 32 columns x 16 B apart
+      uint32_t a_off[D][2];
+#pragma unroll
+      for (int b = 0; b < D; ++b)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) a_off[b][kk] = ((uint32_t)(b * 4 + kk * 2) * lbo) >> 4;
+      int it = 0, unit = -1;
+      for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        if (w.first_of_unit()) {
+          ++unit;
+          ptx::mbar_wait(b_full(unit & 1), (unit >> 1) & 1);
+        }
+        ptx::mbar_wait(xp_full(s), ph);
+        ptx::mbar_wait(t_empty(s), ph ^ 1);
+        ptx::tcgen05_fence_after();
+        const uint32_t a_base = (((smem_base + xp_off + s * xp_bytes) & 0x3FFFF) >> 4) | a_lbo;
+        const uint32_t b_base = (((smem_base + tz_off + (unit & 1) * tz_bytes) & 0x3FFFF) >> 4) | b_lbo;
+        const uint32_t d0 = tmem_base + (uint32_t)s * 256u;
+        if (!(p.dbg & 2)) {
+#pragma unroll 1
+          for (int u = 0; u < p.k; ++u) {
+            const uint32_t a_u = a_base + (uint32_t)(u * p.dil);       // tap row u: u*d rows of 16 bytes further down
+            const uint32_t b_u = b_base + (uint32_t)u * (C2_TZ >> 4);
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+              ptx::umma_f16_ss(d0 + b * 32, a_u + a_off[b][0], hi, b_u, hi, idesc, u ? 1u : 0u);
+              if (p.ks > 1) ptx::umma_f16_ss(d0 + b * 32, a_u + a_off[b][1], hi, b_u + (1024u >> 4), hi, idesc, 1u);
+            }
+          }
+        }
+        ptx::umma_commit(xp_empty(s));
+        ptx::umma_commit(t_full(s));
+      }
+    }
+  } else if (warp <= 5) {
+    // ===== regrouping (128 threads, thread = plane row) + Toeplitz tiles =====
+    const int r = threadIdx.x - 64;
+    const int nchunks = p.W >> 3;  // 16-byte chunks per plane row
+    auto build_t = [&](int c, int s) {
+      const float *wc = p.w + (long)c * p.k * p.k;
+      uint8_t *ts = smem_gen + tz_off + (size_t)s * tz_bytes;
+      // (tap row u, output phase-column q): tap v sits at reduction index q' = q - p/d + v
+      for (int idx = r; idx < ((p.dbg & 1) ? 0 : p.k * 32); idx += 128) {
+        const int u = idx >> 5, q = idx & 31;
+        const float *wr = wc + (p.flip ? (p.k - 1 - u) * p.k : u * p.k);
+        float wv[9];
+#pragma unroll
+        for (int v = 0; v < 9; ++v) wv[v] = v < p.k ? __ldg(wr + (p.flip ? p.k - 1 - v : v)) : 0.f;
+#pragma unroll
+        for (int v = 0; v < 9; ++v) {
+          const int qp = q - p.qoff + v;
+          if (v < p.k && qp >= 0 && qp < 32)
+            *reinterpret_cast<__nv_bfloat16 *>(ts + u * C2_TZ + (qp >> 3) * 512 + q * 16 + (qp & 7) * 2) = __float2bfloat16_rn(wv[v]);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(b_full(s));
+    };
+    int it = 0, unit = -1, built = 0;
+    PlaneWalk ahead(p.pairs, p.planes, p.splits, p.C);  // first plane of the next unit whose tiles are not built yet
+    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      // the MMAs of plane it-2 are done: operand buffer s is free
+      ptx::mbar_wait(xp_empty(s), ph ^ 1);
+      if (w.first_of_unit()) {
+        ++unit;
+        if (built == unit) {  // not built ahead (first unit, or the previous unit had a single plane)
+          build_t(w.channel(), unit & 1);
+          ++built;
+          ahead.next_unit();
+        }
+      } else if (built == unit + 1 && ahead.valid()) {
+        // second or later plane of the unit: plane it-2 was the last one that read the other Toeplitz buffer, so
+        // the next unit's tiles are built here, off the critical path
+        build_t(ahead.channel(), (unit + 1) & 1);
+        ++built;
+        ahead.next_unit();
+      }
+      ptx::mbar_wait(stg_full(s), ph);
+      const uint8_t *stg = smem_gen + s * C2_STG;
+      uint8_t *xp = smem_gen + xp_off + (size_t)s * xp_bytes + (size_t)(r + p.pad) * 16;
+      if (!(p.dbg & 8)) {
+#pragma unroll 1
+        for (int g = 0; g * D < nchunks; ++g) {
+          // 8*D consecutive columns of row r -> 8 phase-columns (one 16-byte chunk) of each of the D phases
+          uint32_t in[4 * D];
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            const int c = g * D + j;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (c < nchunks)
+              v = *reinterpret_cast<const uint4 *>(stg + (c >> 3) * (C2_STG / 2) + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+            in[4 * j] = v.x; in[4 * j + 1] = v.y; in[4 * j + 2] = v.z; in[4 * j + 3] = v.w;
+          }
+#pragma unroll
+          for (int b = 0; b < D; ++b) {
+            uint32_t o[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int x0 = D * (2 * m) + b, x1 = D * (2 * m + 1) + b;  // elements of the 8*D-column group
+              const uint32_t sel = ((x0 & 1) ? 0x32u : 0x10u) | ((x1 & 1) ? 0x7600u : 0x5400u);
+              o[m] = __byte_perm(in[x0 >> 1], in[x1 >> 1], sel);
+            }
+            *reinterpret_cast<uint4 *>(xp + (size_t)(b * 4 + g) * lbo) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(xp_full(s));
+        ptx::mbar_arrive(stg_empty(s));
+      }
+    }
+  } else {
+    // ===== epilogue (128 threads, thread = output row = TMEM lane): re-interleave the phases in registers, stage
+    // 32 rows x 8*D columns per warp in shared memory and let TMA store them (coalesced, clips ragged edges) =====
+    const int quad = warp & 3;
+    const int nchunks = p.W >> 3;
+    const uint32_t ob = ob_off + (uint32_t)(warp - 6) * 2 * OB;
+    int it = 0, gi = 0;
+    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+      const int s = it & 1;
+      ptx::mbar_wait(t_full(s), (it >> 1) & 1);
+      ptx::tcgen05_fence_after();
+      const int c = w.channel();
+      const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
+      const uint32_t t_row = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int g = 0; g * D < nchunks; ++g, ++gi) {
+        uint32_t v[D][8];
+#pragma unroll
+        for (int b = 0; b < D; ++b) ptx::tmem_ld_32x32b_x8(t_row + b * 32 + g * 8, v[b]);
+        ptx::tmem_ld_wait();
+        if (gi >= 2) {  // the store that read this staging tile two groups ago has finished reading it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+        const uint32_t tile = ob + (uint32_t)(gi & 1) * OB;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          uint32_t o[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int x0 = 8 * j + 2 * m, x1 = x0 + 1;  // output columns of the group: column x = phase x % D, index x / D
+            o[m] = pack_bf16x2(__uint_as_float(v[x0 % D][x0 / D]) + bias, __uint_as_float(v[x1 % D][x1 / D]) + bias);
+          }
+          *reinterpret_cast<uint4 *>(smem_gen + tile + lane * (16 * D) + 16 * j) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(p.dbg & 4)) {
+          ptx::tma_store_4d(&tm_out, smem_base + tile, 8 * D * g, 32 * quad, c, w.pl);
+          ptx::tma_store_commit();
+        }
+      }
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(t_empty(s));
+    }
+    if (lane == 0) ptx::tma_store_wait_all();
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool dw_tc_conv2_supported(int Hi, int Wi, int Ho, int Wo, int k, int dil, int pad) {
+  if (getenv("KDCC_DW_CONV_V1")) return false;
+  const int halo = dil * (k - 1);
+  if (Hi != Ho || Wi != Wo || Hi > 128 || Wi > 128 || Wi % 8 != 0) return false;
+  if (k % 2 == 0 || k > 9 || halo > 48 || 2 * pad != halo || pad % dil != 0) return false;
+  if (dil != 1 && dil != 2 && dil != 5) return false;   // instantiated phase counts
+  return (Wi + dil - 1) / dil <= 32;                     // one phase fits the 32-wide reduction
+}
+
+template <int D>
+static int conv2_launch(const void *in, C2Params p, cudaStream_t st) {
+  CUtensorMap tm;
+  const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.C, (uint64_t)p.N};
+  const uint64_t strides[3] = {(uint64_t)p.W * 2, (uint64_t)p.H * p.W * 2, (uint64_t)p.C * p.H * p.W * 2};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  int rc = make_tmap_bf16(&tm, in, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  CUtensorMap tm_out;
+  const uint32_t obox[4] = {8 * D, 32, 1, 1};
+  rc = make_tmap_bf16(&tm_out, p.out, 4, dims, strides, obox, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
+  const int smem = 2 * C2_STG + 2 * D * 4 * p.rows_p * 16 + 2 * p.k * C2_TZ + 128 + 8 * 32 * 16 * D + 256 + 1024;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(dw_tc_conv2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_smem = smem;
+  }
+  const int grid = (int)min(p.pairs, (long)kNumSMs);
+  dw_tc_conv2_kernel<D><<<grid, C2_THREADS, smem, st>>>(tm, tm_out, p);
+  return launch_status();
+}
+
+int dw_tc_conv2(const void *in, const float *w, const float *bias, void *out, int N, int C, int H, int W, int k, int dil,
+                int pad, int flip, cudaStream_t st) {
+  C2Params p{};
+  p.N = N; p.C = C; p.H = H; p.W = W; p.k = k; p.dil = dil; p.pad = pad; p.flip = flip;
+  p.rows_p = 128 + dil * (k - 1);
+  p.ks = ((W + dil - 1) / dil + 15) / 16;
+  p.qoff = pad / dil;
+  p.planes = N;
+  p.splits = tc_unit_splits(C, N);
+  p.pairs = (long)C * p.splits;
+  p.w = w; p.bias = bias;
+  p.out = static_cast<__nv_bfloat16 *>(out);
+  if (N == 0 || C == 0) return KDCC_OK;
+  const char *dbg = getenv("KDCC_TC_DEBUG");
+  p.dbg = dbg ? atoi(dbg) : 0;
+  switch (dil) {
+    case 1: return conv2_launch<1>(in, p, st);
+    case 2: return conv2_launch<2>(in, p, st);
+    case 5: return conv2_launch<5>(in, p, st);
+    default: return KDCC_ESHAPE;
+  }
+}
+
+}  // namespace kdcc
