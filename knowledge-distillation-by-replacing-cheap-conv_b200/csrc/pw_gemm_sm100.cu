@@ -16,6 +16,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one lane),
 // warps 2..5 = epilogue (one TMEM lane quadrant each).  Persistent CTAs walk work items round-robin;
 // the accumulator is double-buffered in TMEM so the epilogue of item n overlaps the MMAs of item n+1.
+#include <stdlib.h>
+
 #include "kdcc_common.cuh"
 #include "pw_kernels.cuh"
 #include "sm100_ptx.cuh"
@@ -42,6 +44,7 @@ struct GemmParams {
   const float *scale, *shift;        // per j, may be null
   int relu;
   float *out_f32;                    // [splits][I][J] fp32 partials (dW) -- exclusive with the bf16 outputs
+  int tma_out;                       // out_raw only: the epilogue stages 32 x 64 tiles in smem and TMA stores them
 };
 
 template <int BJ>
@@ -51,7 +54,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BJ == 256 ? 4 : (BJ == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BJ;  // double-buffered accumulator (power of two >= 32)
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;   // epilogue staging: 4 warps x 2 tiles of 32 rows x 128 bytes
+  static constexpr int BAR_OFF = OUT_OFF + 4 * 2 * 4096;
   static constexpr int SMEM = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
 };
 
@@ -80,7 +84,7 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc() {
 template <int BJ, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                     const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   using Cfg = GemmCfg<BJ>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -101,6 +105,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tm_a);
     ptx::prefetch_tensormap(&tm_b);
+    if (p.tma_out) ptx::prefetch_tensormap(&tm_out);
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)));
   ptx::tcgen05_fence_before();
@@ -181,16 +186,58 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     // ===== epilogue: TMEM -> registers -> global =====
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
     int as = 0; uint32_t aph = 0;
+    const uint32_t stage_tiles = Cfg::OUT_OFF + (uint32_t)(warp - 2) * 2 * 4096;
+    int tn = 0;  // staging tiles written by this warp
     for (long item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = (int)(item % p.splits);
       long tile = item / p.splits;
       const int tj = (int)(tile % p.tiles_j); tile /= p.tiles_j;
       const int ti = (int)(tile % p.tiles_i);
-      const long obase = (long)(tile / p.tiles_i) * p.out_batch_stride;
+      const long tile_batch = tile / p.tiles_i;
+      const long obase = tile_batch * p.out_batch_stride;
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tcgen05_fence_after();
       const int row = ti * GEMM_BI + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (uint32_t)(as * BJ) + ((uint32_t)(quad * 32) << 16);
+      if (p.tma_out) {
+        // bf16 output through shared memory: 32 rows x 64 columns per warp and chunk, 128B-swizzled, stored by TMA
+        // (coalesced 128-byte rows; ragged edges are clipped by the tensor map)
+#pragma unroll 1
+        for (int ch = 0; ch < BJ / 64; ++ch) {
+          const int col0 = tj * BJ + ch * 64;
+          if (col0 >= p.J) break;
+          uint32_t v[64];
+          ptx::tmem_ld_32x32b_x32(t_row + ch * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          ptx::tmem_ld_32x32b_x32(t_row + ch * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          ptx::tmem_ld_wait();
+          if (tn >= 2) {  // the store that read this tile two chunks ago has finished reading it
+            if (lane == 0) ptx::tma_store_wait_read1();
+            __syncwarp();
+          }
+          const uint32_t tile = stage_tiles + (uint32_t)(tn & 1) * 4096;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+            *reinterpret_cast<uint4 *>(smem_gen + tile + lane * 128 + ((c ^ (lane & 7)) << 4)) = o;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_3d(&tm_out, smem_base + tile, col0, ti * GEMM_BI + quad * 32, (int)(tile_batch));
+            ptx::tma_store_commit();
+          }
+          ++tn;
+        }
+        ptx::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        if (++as == 2) { as = 0; aph ^= 1; }
+        continue;
+      }
 #pragma unroll 1
       for (int ch = 0; ch < BJ / 32; ++ch) {
         uint32_t v[32];
@@ -247,6 +294,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (p.tma_out && lane == 0) ptx::tma_store_wait_all();
   }
 
   ptx::tcgen05_fence_before();
@@ -293,6 +341,18 @@ static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaS
   if (rc) return rc;
   rc = B_MN ? gemm_map(&tm_b, b, p.J, p.R, bb, 64) : gemm_map(&tm_b, b, p.R, p.J, bb, BJ);
   if (rc) return rc;
+  // bf16 raw output only: TMA-store epilogue over out[batch][I][J]
+  CUtensorMap tm_out = tm_a;
+  p.tma_out = 0;
+  if (p.out_raw && !p.out_act && !p.out_f32 && !getenv("KDCC_PW_DIRECT_STORE")) {
+    const int ob = p.r_spans_batch ? 1 : p.batch;
+    const uint64_t dims[3] = {(uint64_t)p.J, (uint64_t)p.I, (uint64_t)ob};
+    const uint64_t strides[2] = {(uint64_t)p.J * 2, (uint64_t)(ob > 1 ? p.out_batch_stride : (long)p.I * p.J) * 2};
+    const uint32_t box[3] = {64, 32, 1};
+    rc = make_tmap_bf16(&tm_out, p.out_raw, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    p.tma_out = 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pw_gemm_sm100_kernel<BJ, A_MN, B_MN>,
@@ -302,7 +362,7 @@ static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaS
   }
   const long items = (long)p.tiles_i * p.tiles_j * p.splits * (p.r_spans_batch ? 1 : p.batch);
   const int grid = (int)min(items, (long)kNumSMs);
-  pw_gemm_sm100_kernel<BJ, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(tm_a, tm_b, p);
+  pw_gemm_sm100_kernel<BJ, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(tm_a, tm_b, tm_out, p);
   return launch_status();
 }
 

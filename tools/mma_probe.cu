@@ -23,6 +23,9 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint32_t a_lo, uint32_t a_hi,
       "r"(idesc), "r"(1u)
       : "memory");
 }
+__device__ __forceinline__ void cp_128x256b(uint32_t tmem_dst, uint32_t lo, uint32_t hi) {
+  asm volatile("{\n.reg .b64 d;\nmov.b64 d, {%1, %2};\ntcgen05.cp.cta_group::1.128x256b [%0], d;\n}\n" ::"r"(tmem_dst), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
   asm volatile(
       "{\n.reg .pred p;\n.reg .b64 db;\nmov.b64 db, {%2, %3};\nsetp.ne.b32 p, %5, 0;\n"
@@ -36,6 +39,7 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_l
 // mode 2: TS, A TMEM, B K-major no-swizzle
 // mode 3: TS, A TMEM, B MN-major SW128                  (dw_tc_wgrad.cu)
 // mode 4: SS, A K-major SW128, B K-major SW128           (plain GEMM)
+// mode 5: tcgen05.cp 128x256b (A slice smem -> TMEM) + TS MMA;  mode 6: the copies alone
 __global__ void __launch_bounds__(128, 1) probe(int mode, int N, int iters, int nacc, long long *out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(128, 1) probe(int mode, int N, int iters, int 
     const uint32_t ns_hi = (128u >> 4) | (1u << 14);
     uint32_t a_lo, a_hi, b_lo, b_hi;
     a_lo = ((a_base & 0x3FFFF) >> 4) | (1u << 16); a_hi = sw_hi;
-    if (mode == 1) { a_lo = ((a_base & 0x3FFFF) >> 4) | ((uint32_t)((168 * 16) >> 4) << 16); a_hi = ns_hi; }
+    if (mode == 1 || mode >= 5) { a_lo = ((a_base & 0x3FFFF) >> 4) | ((uint32_t)((168 * 16) >> 4) << 16); a_hi = ns_hi; }
     b_lo = ((b_base & 0x3FFFF) >> 4) | ((uint32_t)((N * 16) >> 4) << 16); b_hi = ns_hi;
     if (mode == 3) { b_lo = ((b_base & 0x3FFFF) >> 4) | ((uint32_t)((16384) >> 4) << 16); b_hi = sw_hi; }
     if (mode == 4) { b_lo = ((b_base & 0x3FFFF) >> 4) | (1u << 16); b_hi = sw_hi; }
@@ -70,7 +74,11 @@ __global__ void __launch_bounds__(128, 1) probe(int mode, int N, int iters, int 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t d = tmem + (uint32_t)(j % NACC) * (uint32_t)N;
-          if (mode == 2 || mode == 3) mma_ts(d, tmem + 480u + (uint32_t)(j & 1) * 8u, b_lo + (uint32_t)j * 8u, b_hi, idesc);
+          if (mode == 5 || mode == 6) {
+            // copy the next A slice into one of 8 TMEM slots, then multiply from it (mode 6: copies only)
+            cp_128x256b(tmem + 448u + (uint32_t)j * 8u, a_lo + (uint32_t)j * 5u, a_hi);
+            if (mode == 5) mma_ts(d, tmem + 448u + (uint32_t)j * 8u, b_lo + (uint32_t)(j & 1) * 2u, b_hi, idesc);
+          } else if (mode == 2 || mode == 3) mma_ts(d, tmem + 480u + (uint32_t)(j & 1) * 8u, b_lo + (uint32_t)j * 8u, b_hi, idesc);
           else mma_ss(d, a_lo + (mode == 1 ? (uint32_t)j * 5u : (uint32_t)j * 8u), a_hi, b_lo + (uint32_t)(j & 1) * 2u, b_hi, idesc);
         }
       }
@@ -98,10 +106,12 @@ int main() {
   const int iters = 4096;
   const int Ns[] = {32, 64, 128, 176, 256};
   const int accs[] = {1, 2, 4, 8};
-  for (int mode = 0; mode < 5; ++mode)
+  for (int mode = 0; mode < 7; ++mode)
     for (int N : Ns) for (int nacc : accs) {
       if (N == 176 && mode != 3 && mode != 2) continue;
       if (nacc * N > 448) continue;
+      if (mode >= 5 && N != 32) continue;
+      if (mode < 5 && !(N == 32 && nacc == 4)) continue;
       for (int rep = 0; rep < 2; ++rep) {
         probe<<<148, 128, 200 * 1024>>>(mode, N, iters, nacc, d_out);
         cudaError_t e = cudaDeviceSynchronize();
