@@ -343,11 +343,26 @@ def run_kdcc(args, rank, world, local_rank):
                 dominant, dom_ms = name, per_step_ms
         kernels[name] = entry
     dk = kernels[dominant]
+    # measured DRAM traffic of the dominant family over one step: ncu dram__bytes_read.sum + dram__bytes_write.sum of
+    # every launch of one step of this same default workload (tools/gpu_profile.sh -> profiles/r01_traffic.json)
+    traffic = None
+    try:
+        if (N, args.dw, args.layout, args.crop) == (4, "k9d5p20", "nchw", 1024):
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = json.load(f)["families"][dominant]["dram_bytes_per_step"]
+    except Exception:
+        traffic = None
+    note = ""
+    if dominant.startswith("dw") and k >= 7:
+        note = ("achieved = algorithmic bytes of all %d launches of one step / their CUDA-event time; traffic = ncu DRAM bytes of the "
+                "same launches.  k=9 depthwise is 81 MAC per output element (20 MAC per HBM byte): the kernels run on tcgen05 and are "
+                "bound by the issue cost of their small-N MMAs (90 x 59 clk conv, 72 x 74 clk dW per plane, DESIGN.md 4.0/4.1), "
+                "not by HBM; frac is still reported against the HBM copy peak" % dk["launches_per_step"])
     roofline = {"kernel": dominant, "bound": dk["bound"], "achieved": dk["achieved"],
                 "peak": pk["hbm_gbs"] if dk["bound"] == "hbm" else pk["bf16_tflops_sustained"], "unit": dk["unit"],
-                "frac": dk["frac"], "traffic": None, "peak_source": pk["source"] + (" copy bandwidth" if dk["bound"] == "hbm" else " sustained cuBLAS bf16"),
-                "note": ("k=9 depthwise is 81 MAC per output element: CUDA-core FFMA-bound, not HBM-bound (see DESIGN.md); "
-                         "frac is still reported against the HBM copy peak") if dominant.startswith("dw") and k >= 7 else ""}
+                "frac": dk["frac"], "traffic": traffic, "algorithmic_bytes": alg[dominant][0] if alg[dominant][1] == "B" else None,
+                "peak_source": pk["source"] + (" copy bandwidth" if dk["bound"] == "hbm" else " sustained cuBLAS bf16"),
+                "note": note}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

@@ -123,9 +123,10 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     for (long item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = (int)(item % p.splits);
       long tile = item / p.splits;
-      const int tj = (int)(tile % p.tiles_j); tile /= p.tiles_j;
-      const int ti = (int)(tile % p.tiles_i);
-      const int bo = (int)(tile / p.tiles_i);  // output batch entry
+      // i fastest: CTAs running side by side share the (large) B tile and differ in the (small, L2-resident) A tile
+      const int ti = (int)(tile % p.tiles_i); tile /= p.tiles_i;
+      const int tj = (int)(tile % p.tiles_j);
+      const int bo = (int)(tile / p.tiles_j);  // output batch entry
       const int rb0 = split * rb_per_split, rb1 = min(p.rblocks, rb0 + rb_per_split);
       for (int rb = rb0; rb < rb1; ++rb) {
         // reduction block -> (batch entry, block inside the entry)
@@ -191,9 +192,9 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     for (long item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = (int)(item % p.splits);
       long tile = item / p.splits;
-      const int tj = (int)(tile % p.tiles_j); tile /= p.tiles_j;
-      const int ti = (int)(tile % p.tiles_i);
-      const long tile_batch = tile / p.tiles_i;
+      const int ti = (int)(tile % p.tiles_i); tile /= p.tiles_i;
+      const int tj = (int)(tile % p.tiles_j);
+      const long tile_batch = tile / p.tiles_j;
       const long obase = tile_batch * p.out_batch_stride;
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tcgen05_fence_after();
