@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KDCC_VERSION 101 /* round 1, layout-aware depthwise/pointwise */
+#define KDCC_VERSION 102 /* round 1: layout-aware depthwise/pointwise, confusion matrix */
 
 enum { KDCC_F32 = 0, KDCC_BF16 = 1 };
 enum { KDCC_LAYOUT_NHWC = 0, KDCC_LAYOUT_NCHW = 1 };
@@ -126,6 +126,16 @@ int kdcc_scale_inplace(void *buf, const float *dev_scalar, long n, int dtype, kd
 int kdcc_colsum(const void *a, float *out, void *workspace, size_t workspace_bytes, long M, int Nc,
                 int dtype, kdcc_stream_t stream);
 size_t kdcc_colsum_workspace_bytes(long M, int Nc);
+
+/* ---- segmentation metric --------------------------------------------------------
+ * kdcc_confusion_update replaces utils/util.py:108-128 (CityscapesMetricTracker.update ->
+ * confusion_for_batch) and models/metric.py:49-55: pred = argmax_c logits[n][c][q] (first maximum),
+ * conf[labels[n][q]][pred] += 1 for labels in [0, C) and != ignore_index.  logits element (n,c,q) at
+ * base + n*batch_stride + c*class_stride + q; labels int64 [N][HW]; conf int64 [C][C] on the device,
+ * ACCUMULATED (zero it to reset).  One HBM pass, no host copy; C <= 32. */
+int kdcc_confusion_update(const void *logits, const long long *labels, long long *conf, int N, int C, long HW,
+                          long batch_stride, long class_stride, int ignore_index, int dtype,
+                          kdcc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,8 @@ from .blocks import DepthwiseSeparableBlock
 from .losses import EnsembleKLDivergenceLoss, KLDivergenceLoss, MSELoss, WeightedHintMSELoss
 from . import functional
 from .student import DepthwiseStudent
-from .trainer import ConfusionMatrix, GradBucket, LayerwiseStep
+from .metrics import CityscapesMetricTracker, ConfusionMatrix
+from .trainer import GradBucket, LayerwiseStep
 
-__all__ = ["DepthwiseSeparableBlock", "DepthwiseStudent", "LayerwiseStep", "GradBucket", "ConfusionMatrix", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
+__all__ = ["DepthwiseSeparableBlock", "DepthwiseStudent", "LayerwiseStep", "GradBucket", "ConfusionMatrix", "CityscapesMetricTracker", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
            "functional", "KdccError", "LIB_PATH"]

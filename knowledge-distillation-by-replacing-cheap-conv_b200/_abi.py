@@ -34,6 +34,7 @@ SIGNATURES = {
     "kdcc_scale_inplace": (_i, [_vp, _vp, _l, _i, _vp]),
     "kdcc_colsum": (_i, [_vp, _vp, _vp, _sz, _l, _i, _i, _vp]),
     "kdcc_colsum_workspace_bytes": (_sz, [_l, _i]),
+    "kdcc_confusion_update": (_i, [_vp, _vp, _vp, _i, _i, _l, _l, _l, _i, _i, _vp]),
 }
 
 _lib = None

@@ -300,3 +300,29 @@ class _HintLoss(torch.autograd.Function):
 def hint_loss(inputs, targets, filter_weight=None, scale=1.0):
     """scale/N * sum_n [sum_c w mean_hw (s-t)^2 / sum_c w]; filter_weight None = uniform (MSELoss)."""
     return _HintLoss.apply(inputs, targets, filter_weight, float(scale))
+
+
+# ---------------------------------------------------------------------------------------------------
+# segmentation metric (SURVEY.md 8f n1)
+# ---------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def confusion_update(conf, logits, target, ignore_index=255):
+    """conf (C*C int64, device) += confusion matrix of argmax(logits, 1) against target -- utils/util.py:108-128.
+    One kernel pass over the logits and labels; nothing is copied to the host."""
+    _require_cuda(conf, logits, target)
+    if conf.dtype != torch.int64 or not conf.is_contiguous():
+        raise _abi.KdccError("confusion_update needs a contiguous int64 accumulator")
+    N, C = logits.shape[0], logits.shape[1]
+    if conf.numel() != C * C:
+        raise _abi.KdccError("accumulator has %d cells, logits have %d classes" % (conf.numel(), C))
+    logits = logits.detach().contiguous()
+    target = target.detach()
+    if target.dtype != torch.int64:
+        target = target.long()
+    target = target.contiguous()
+    HW = logits.numel() // max(1, N * C)
+    if target.numel() != N * HW:
+        raise _abi.KdccError("labels have %d elements, logits describe %d pixels" % (target.numel(), N * HW))
+    _abi.check(_abi.lib().kdcc_confusion_update(_ptr(logits), _ptr(target), _ptr(conf), N, C, HW, C * HW, HW, int(ignore_index),
+                                                _dtype_code(logits), _stream()), "kdcc_confusion_update")
+    return conf

@@ -14,6 +14,8 @@ teacher replicated, eval-mode BN: no other cross-rank coupling).
 from functools import reduce
 
 import torch
+
+from .metrics import ConfusionMatrix  # noqa: F401  (kernel-backed; kept importable from here)
 import torch.distributed as dist
 
 
@@ -43,33 +45,6 @@ class GradBucket:
             else:  # gloo has no AVG
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
                 self.flat.div_(world)
-
-
-class ConfusionMatrix:
-    """Device-side replacement of utils/util.py:108-128 (CityscapesMetricTracker): argmax + bincount stay on
-    the GPU, nothing is copied to the host until `iou()` is asked for."""
-
-    def __init__(self, num_classes=19, ignore_index=255, device="cpu"):
-        self.nc, self.ignore = num_classes, ignore_index
-        self.mat = torch.zeros(num_classes * num_classes, dtype=torch.long, device=device)
-
-    def reset(self):
-        self.mat.zero_()
-
-    @torch.no_grad()
-    def update(self, logits, target):
-        pred = logits.argmax(dim=1).reshape(-1)
-        tgt = target.reshape(-1)
-        keep = (tgt != self.ignore) & (tgt >= 0) & (tgt < self.nc)
-        idx = tgt[keep] * self.nc + pred[keep]
-        self.mat += torch.bincount(idx, minlength=self.nc * self.nc).to(self.mat.device)
-
-    def iou(self):
-        m = self.mat.view(self.nc, self.nc).double()
-        inter = m.diag()
-        union = m.sum(0) + m.sum(1) - inter
-        valid = union > 0
-        return float((inter[valid] / union[valid]).mean()) if valid.any() else 0.0
 
 
 class LayerwiseStep:

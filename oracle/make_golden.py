@@ -60,6 +60,29 @@ def loss_case(tag, module, args, grads_of=0):
     return out
 
 
+def metrics_golden():
+    """utils/util.py CityscapesMetricTracker run on seeded logits/labels (ignore pixels, exact ties, two updates)."""
+    util = _load("ref_util", "utils/util.py")
+    out = {}
+    torch.manual_seed(31)
+    tr = util.CityscapesMetricTracker()
+    cases = []
+    for i, (n, h, w) in enumerate([(2, 37, 53), (1, 64, 64)]):
+        logits = 3 * torch.randn(n, 19, h, w)
+        logits[:, 5] = logits[:, 3]            # exact ties between two classes: the first index must win
+        logits[0, :, 0, :7] = 0.25             # all classes tied
+        labels = torch.randint(0, 19, (n, h, w))
+        labels[torch.rand(n, h, w) < 0.07] = 255
+        cases.append((logits, labels))
+        out["in%d/logits" % i], out["in%d/labels" % i] = logits.numpy(), labels.numpy().copy()
+        tr.update(logits, labels.clone())
+        out["conf_after%d" % i] = tr.conf.astype(np.int64)
+        out["iou_after%d" % i] = np.array(tr.get_iou())
+    tr.reset()
+    out["iou_empty"] = np.array(tr.get_iou())
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # deterministic reduction order
@@ -127,7 +150,8 @@ def main():
     losses.update(loss_case("mse_1x1", mse(num_classes=19), [s4, t4])); losses["mse_1x1/nc"] = np.array(19.0)
     np.savez_compressed(os.path.join(OUT, "losses.npz"), **losses)
 
-    for fn in ("block.npz", "losses.npz"):
+    metrics_golden()
+    for fn in ("block.npz", "losses.npz", "metrics.npz"):
         print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")
 
 

@@ -143,3 +143,26 @@ def block_fwd_bwd(x, w_dw, w_pw, k, d, p, dy=None, need_dx=True):
     dmid, dw_pw, _ = pw_bwd(mid, w_pw, dy)
     dx, dw_dw, _ = dw_bwd(x, w_dw, dmid, k, d, p, need_dx=need_dx)
     return y, dx, dw_dw, dw_pw
+
+
+def confusion(outputs, labels, num_classes=None, ignore_index=255):
+    """Confusion matrix of argmax(outputs, axis 1) against labels, numpy restatement of
+    utils/util.py:108-128 (CityscapesMetricTracker.update + confusion_for_batch): labels == ignore_index are
+    rewritten to num_classes and masked out, hist[target][pred] = bincount(C * target + pred).  int64 (C, C)."""
+    outputs, labels = np.asarray(outputs), np.asarray(labels).copy()
+    C = outputs.shape[1] if num_classes is None else num_classes
+    labels[labels == ignore_index] = C
+    pred = outputs.argmax(axis=1).reshape(-1)
+    target = labels.reshape(-1)
+    mask = (target >= 0) & (target < C)
+    return np.bincount(C * target[mask].astype(np.int64) + pred[mask], minlength=C * C).reshape(C, C).astype(np.int64)
+
+
+def mean_iou(conf):
+    """utils/util.py:113-118 (get_iou): nanmean of tp / (rows + cols - tp); 1.0 for an all-zero matrix."""
+    conf = np.asarray(conf, np.float64)
+    if not np.any(conf):
+        return 1.0
+    tp = np.diag(conf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.nanmean(tp / (conf.sum(0) + conf.sum(1) - tp)))
