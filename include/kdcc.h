@@ -107,6 +107,17 @@ int kdcc_kd_loss(const void *s, const void *t, void *ds, float *loss_out, void *
                  long pixel_stride, float T, int target_is_prob, int dtype, float grad_scale,
                  kdcc_stream_t stream);
 
+/* kdcc_kd_loss_multi replaces the K+1 criterion calls of trainer/ensemble_trainer.py:76-83
+ * (kd_loss = sum_k WEIGHT*KL(s, t_k) + KL(s, t_teacher), every term a losses/KLDiv.py KLDivergenceLoss):
+ *   *loss_out = sum_k weights[k] * T^2/(N*HW) * sum_pix KL(softmax(t_k/T) || softmax(s/T))
+ *   ds        = grad_scale * T/(N*HW) * ( (sum_k weights[k]) softmax(s/T) - sum_k weights[k] softmax(t_k/T) )
+ * in ONE pass that reads s once and each teacher once.  `teachers` and `weights` are HOST arrays of K (<= 8) device
+ * pointers / floats (copied into the kernel parameters); all tensors share dtype and strides.  C <= 32. */
+int kdcc_kd_loss_multi(const void *s, const void *const *teachers, const float *weights, int K, void *ds,
+                       float *loss_out, void *workspace, size_t workspace_bytes, int N, int C, long HW,
+                       long batch_stride, long class_stride, long pixel_stride, float T, int dtype,
+                       float grad_scale, kdcc_stream_t stream);
+
 /* kdcc_hint_loss replaces losses/WeightedHintMSELoss.py:12-16 (w given, scale = 1) and
  * losses/MSELoss.py:14-16 (w NULL, scale = num_classes):
  *   *loss_out = scale/N * sum_n [ sum_c w[n,c] mean_hw (s-t)^2 / sum_c w[n,c] ]

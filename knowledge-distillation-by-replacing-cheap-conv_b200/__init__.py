@@ -7,11 +7,11 @@ Host-side mirror of the reference's module interfaces over the C-ABI library lib
 from . import _abi
 from ._abi import KdccError, LIB_PATH
 from .blocks import DepthwiseSeparableBlock
-from .losses import EnsembleKLDivergenceLoss, KLDivergenceLoss, MSELoss, WeightedHintMSELoss
+from .losses import EnsembleKLDivergenceLoss, KLDivergenceLoss, MSELoss, MultiTeacherKLDivergenceLoss, WeightedHintMSELoss
 from . import functional
 from .student import DepthwiseStudent
 from .metrics import CityscapesMetricTracker, ConfusionMatrix
 from .trainer import GradBucket, LayerwiseStep
 
-__all__ = ["DepthwiseSeparableBlock", "DepthwiseStudent", "LayerwiseStep", "GradBucket", "ConfusionMatrix", "CityscapesMetricTracker", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
+__all__ = ["DepthwiseSeparableBlock", "DepthwiseStudent", "LayerwiseStep", "GradBucket", "ConfusionMatrix", "CityscapesMetricTracker", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MultiTeacherKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
            "functional", "KdccError", "LIB_PATH"]

@@ -139,6 +139,117 @@ __global__ void __launch_bounds__(kLossThreads) kd_loss_kernel(const KdParams p)
   if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-teacher KD (trainer/ensemble_trainer.py:76-83): the student logits are read ONCE, every
+// teacher's softmax is formed in registers, and
+//     loss = sum_k w_k * T^2/(N*HW) * sum_pix KL(p_k || p_s)
+//          = T^2/(N*HW) * sum_pix [ sum_k w_k sum_c p_kc log p_kc  -  sum_c (sum_k w_k p_kc) log p_sc ]
+//     ds   = grad_scale * T/(N*HW) * ( (sum_k w_k) softmax(s/T) - sum_k w_k p_k )
+// Traffic K+2 tensors instead of the 3K of K separate kdcc_kd_loss calls.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxTeachers = 8;
+struct KdMultiParams {
+  const void *s;
+  const void *t[kMaxTeachers];
+  float w[kMaxTeachers];
+  float wsum;
+  int K;
+  void *ds;
+  float *partials;
+  long HW, bs, cs, ps;
+  long groups, HWg;
+  int C;
+  float k2, gcoef;
+};
+
+template <typename T, int CT, bool EXACT, int PIX>
+__global__ void __launch_bounds__(kLossThreads) kd_multi_kernel(const KdMultiParams p) {
+  __shared__ float scratch[32];
+  const T *__restrict__ sbase = static_cast<const T *>(p.s);
+  T *__restrict__ dbase = static_cast<T *>(p.ds);
+  const int C = EXACT ? CT : p.C;
+  float local = 0.f;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < p.groups; g += (long)gridDim.x * blockDim.x) {
+    const long n = g / p.HWg;
+    const long q = (g - n * p.HWg) * PIX;
+    const long off = n * p.bs + q * p.ps;
+    float sv[CT][PIX], pw[CT][PIX];  // student log2-probabilities, weighted teacher probabilities
+    float ent[PIX];                  // sum_k w_k sum_c p_kc log2 p_kc
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+      if (EXACT || c < C) load_pix<T, PIX>(sbase + off + c * p.cs, sv[c]);
+#pragma unroll
+    for (int i = 0; i < PIX; ++i) {
+      float smax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) smax = fmaxf(smax, sv[c][i]);
+      float ssum = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) {
+          sv[c][i] = (sv[c][i] - smax) * p.k2;
+          ssum += exp2f(sv[c][i]);
+          pw[c][i] = 0.f;
+        }
+      const float ls = log2f(ssum);
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) sv[c][i] -= ls;  // log2 p_s
+      ent[i] = 0.f;
+    }
+    for (int k = 0; k < p.K; ++k) {
+      const T *__restrict__ tbase = static_cast<const T *>(p.t[k]);
+      const float wk = p.w[k];
+      float tv[CT][PIX];
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) load_pix<T, PIX>(tbase + off + c * p.cs, tv[c]);
+#pragma unroll
+      for (int i = 0; i < PIX; ++i) {
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (EXACT || c < C) tmax = fmaxf(tmax, tv[c][i]);
+        float tsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (EXACT || c < C) {
+            tv[c][i] = (tv[c][i] - tmax) * p.k2;
+            tsum += exp2f(tv[c][i]);
+          }
+        const float lt = log2f(tsum);
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (EXACT || c < C) {
+            const float lpt = tv[c][i] - lt;
+            const float pt = exp2f(lpt);
+            if (pt > 0.f) ent[i] += wk * pt * lpt;
+            pw[c][i] += wk * pt;
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PIX; ++i) {
+      float cross = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) {
+          if (pw[c][i] > 0.f) cross += pw[c][i] * sv[c][i];
+          sv[c][i] = p.gcoef * (p.wsum * exp2f(sv[c][i]) - pw[c][i]);
+        }
+      local += ent[i] - cross;
+    }
+    if (dbase != nullptr) {
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) store_pix<T, PIX>(dbase + off + c * p.cs, sv[c]);
+    }
+  }
+  const float tot = block_sum(local, scratch);
+  if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
+}
+
 // Any class count: three passes over the class axis per pixel (re-reads hit L1/L2).
 template <typename T>
 __global__ void __launch_bounds__(kLossThreads) kd_loss_generic_kernel(const KdParams p) {
@@ -428,6 +539,62 @@ KDCC_API int kdcc_kd_loss(const void *s, const void *t, void *ds, float *loss_ou
   if (rc) return rc;
   const double coef = (double)kLn2 * (double)T * (double)T / ((double)N * (double)HW);
   loss_finalize_kernel<<<1, 256, 0, st>>>(p.partials, used, coef, loss_out);
+  return launch_status();
+}
+
+template <typename T>
+static void launch_kd_multi(const KdMultiParams &p, bool vec2, int grid, cudaStream_t st) {
+#define KDM_LAUNCH(CT, EXACT)                                                             \
+  do {                                                                                    \
+    if (vec2 && CT <= 10) kd_multi_kernel<T, CT, EXACT, 2><<<grid, kLossThreads, 0, st>>>(p); \
+    else kd_multi_kernel<T, CT, EXACT, 1><<<grid, kLossThreads, 0, st>>>(p);              \
+  } while (0)
+  if (p.C == 19) KDM_LAUNCH(19, true);
+  else if (p.C == 10) KDM_LAUNCH(10, true);
+  else if (p.C <= 16) KDM_LAUNCH(16, false);
+  else KDM_LAUNCH(32, false);
+#undef KDM_LAUNCH
+}
+
+KDCC_API int kdcc_kd_loss_multi(const void *s, const void *const *teachers, const float *weights, int K, void *ds,
+                                float *loss_out, void *workspace, size_t workspace_bytes, int N, int C, long HW,
+                                long batch_stride, long class_stride, long pixel_stride, float T, int dtype,
+                                float grad_scale, kdcc_stream_t stream) {
+  if (!s || !teachers || !weights || !loss_out || !workspace) return KDCC_EINVAL;
+  if (N <= 0 || C <= 0 || HW <= 0 || !(T > 0.f) || K <= 0) return KDCC_EINVAL;
+  if (dtype != KDCC_F32 && dtype != KDCC_BF16) return KDCC_EINVAL;
+  if (K > kMaxTeachers || C > 32) return KDCC_ESHAPE;
+  if (workspace_bytes < kdcc_loss_workspace_bytes()) return KDCC_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t esz = dtype == KDCC_F32 ? 4 : 2;
+  KdMultiParams p{};
+  p.s = s; p.ds = ds; p.K = K;
+  p.partials = static_cast<float *>(workspace);
+  p.HW = HW; p.bs = batch_stride; p.cs = class_stride; p.ps = pixel_stride; p.C = C;
+  p.k2 = kLog2e / T;
+  p.gcoef = (float)((double)grad_scale * (double)T / ((double)N * (double)HW));
+  const size_t valign = 2 * esz;
+  bool vec2 = pixel_stride == 1 && (HW % 2 == 0) && (batch_stride % 2 == 0) && (class_stride % 2 == 0) &&
+              ((uintptr_t)s % valign == 0) && (ds == nullptr || (uintptr_t)ds % valign == 0);
+  double wsum = 0.0;
+  for (int k = 0; k < K; ++k) {
+    if (!teachers[k]) return KDCC_EINVAL;
+    p.t[k] = teachers[k];
+    p.w[k] = weights[k];
+    wsum += weights[k];
+    vec2 = vec2 && ((uintptr_t)teachers[k] % valign == 0);
+  }
+  p.wsum = (float)wsum;
+  vec2 = vec2 && C == 10;  // three C x PIX register arrays: two pixels per thread only fit for the small class count
+  p.HWg = vec2 ? HW / 2 : HW;
+  p.groups = (long)N * p.HWg;
+  const int grid = (int)min((long)kMaxLossBlocks, ceil_div<long>(p.groups, kLossThreads));
+  if (dtype == KDCC_F32) launch_kd_multi<float>(p, vec2, grid, st);
+  else launch_kd_multi<__nv_bfloat16>(p, vec2, grid, st);
+  int rc = launch_status();
+  if (rc) return rc;
+  const double coef = (double)kLn2 * (double)T * (double)T / ((double)N * (double)HW);
+  loss_finalize_kernel<<<1, 256, 0, st>>>(p.partials, grid, coef, loss_out);
   return launch_status();
 }
 

@@ -251,6 +251,57 @@ def kd_loss(inputs, targets, temperature=1.0, target_is_prob=False):
     return _KdLoss.apply(inputs, targets, float(temperature), bool(target_is_prob))
 
 
+class _KdLossMulti(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, temperature, weights, *teachers):
+        import ctypes
+        _require_cuda(s, *teachers)
+        K = len(teachers)
+        if K == 0 or K != len(weights):
+            raise _abi.KdccError("kd_loss_multi needs one weight per teacher (got %d teachers, %d weights)" % (K, len(weights)))
+        for t in teachers:
+            if t.shape != s.shape:
+                raise _abi.KdccError("kd_loss_multi expects matching (N, C, ...) tensors, got %s and %s" % (tuple(s.shape), tuple(t.shape)))
+        s = s.detach()
+        if s.dim() == 4 and s.is_contiguous(memory_format=torch.channels_last) and not s.is_contiguous():
+            fmt = torch.channels_last
+        else:
+            fmt = torch.contiguous_format
+            s = s.contiguous()
+        ts = [t.detach().to(s.dtype).contiguous(memory_format=fmt) for t in teachers]
+        N, C, HW, bs, cs, ps = _logit_strides(s)
+        need_grad = ctx.needs_input_grad[0]
+        ds = torch.empty_like(s) if need_grad else None
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        L = _abi.lib()
+        ws = _workspace(L.kdcc_loss_workspace_bytes(), s.device)
+        ptrs = (ctypes.c_void_p * K)(*[t.data_ptr() for t in ts])
+        wts = (ctypes.c_float * K)(*[float(w) for w in weights])
+        _abi.check(L.kdcc_kd_loss_multi(_ptr(s), ptrs, wts, K, _ptr(ds), _ptr(loss), _ptr(ws), ws.numel(), N, C, HW, bs, cs, ps,
+                                        float(temperature), _dtype_code(s), 1.0, _stream()), "kdcc_kd_loss_multi")
+        ctx.ds = ds
+        ctx.K = K
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        ds = ctx.ds
+        if ds is None:
+            return (None,) * (3 + ctx.K)
+        g = g.detach().float().contiguous()
+        _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
+                   "kdcc_scale_inplace")
+        ctx.ds = None
+        return (ds,) + (None,) * (2 + ctx.K)
+
+
+def kd_loss_multi(inputs, teachers, weights, temperature=1.0):
+    """sum_k weights[k] * T^2/(N*HW) * sum_pix KL(softmax(teachers[k]/T) || softmax(inputs/T)) in one pass over the
+    student logits (trainer/ensemble_trainer.py:76-83); fp32 0-dim tensor with grad_fn."""
+    teachers = list(teachers)
+    return _KdLossMulti.apply(inputs, float(temperature), tuple(float(w) for w in weights), *teachers)
+
+
 class _HintLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, s, t, weight, scale):

@@ -54,3 +54,24 @@ class WeightedHintMSELoss(nn.Module):
 
     def forward(self, inputs, targets, filter_weight):
         return F_kdcc.hint_loss(inputs, targets, filter_weight, scale=1.0)
+
+
+class MultiTeacherKLDivergenceLoss(nn.Module):
+    """The KD term of trainer/ensemble_trainer.py:76-83 as one module:
+        (sum_k WEIGHT * KL_T(student, ensemble_k) + KL_T(student, teacher)) / (WEIGHT * K + 1)
+    with every KL a losses/KLDiv.py KLDivergenceLoss(temperature).  One fused pass reads the student logits once and
+    each teacher once (kdcc_kd_loss_multi) instead of K + 1 criterion calls."""
+
+    def __init__(self, temperature=1, weight=1):
+        super().__init__()
+        self.temperature = temperature
+        self.weight = weight  # WEIGHT of trainer/ensemble_trainer.py:10
+
+    def forward(self, inputs, ensemble_outputs, teacher_output=None):
+        outs = list(ensemble_outputs)
+        w = [float(self.weight)] * len(outs)
+        if teacher_output is not None:
+            outs.append(teacher_output)
+            w.append(1.0)
+        total = sum(w)
+        return F_kdcc.kd_loss_multi(inputs, outs, [x / total for x in w], self.temperature)

@@ -60,6 +60,31 @@ def loss_case(tag, module, args, grads_of=0):
     return out
 
 
+def ensemble_golden():
+    """The reference has no module for the multi-teacher KD term: it is the three lines
+    trainer/ensemble_trainer.py:81-83 over its KLDivergenceLoss module, reproduced here with that module."""
+    from functools import reduce
+    kl = _load("ref_kl", "losses/KLDiv.py").KLDivergenceLoss
+    WEIGHT = 1  # trainer/ensemble_trainer.py:10
+    out = {}
+    for tag, shape, T, K in (("seg_T1", (2, 19, 9, 11), 1, 3), ("cifar_T5", (32, 10), 5, 2), ("seg_T2_w", (1, 19, 8, 8), 2, 4)):
+        torch.manual_seed(41 + K)
+        crit = kl(temperature=T)
+        s = (2 * torch.randn(shape)).requires_grad_(True)
+        outputs = [2 * torch.randn(shape) for _ in range(K)]
+        tc = 2 * torch.randn(shape)
+        kd = reduce(lambda acc, elem: acc + WEIGHT * crit(s, elem), outputs, 0)
+        kd = kd + crit(s, tc)
+        kd = kd / (WEIGHT * len(outputs) + 1)
+        kd.backward()
+        out[tag + "/s"] = s.detach().numpy()
+        out[tag + "/teachers"] = np.stack([o.numpy() for o in outputs] + [tc.numpy()])
+        out[tag + "/T"] = np.array(float(T))
+        out[tag + "/loss"] = np.array(float(kd))
+        out[tag + "/ds"] = s.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "ensemble.npz"), **out)
+
+
 def metrics_golden():
     """utils/util.py CityscapesMetricTracker run on seeded logits/labels (ignore pixels, exact ties, two updates)."""
     util = _load("ref_util", "utils/util.py")
@@ -151,7 +176,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "losses.npz"), **losses)
 
     metrics_golden()
-    for fn in ("block.npz", "losses.npz", "metrics.npz"):
+    ensemble_golden()
+    for fn in ("block.npz", "losses.npz", "metrics.npz", "ensemble.npz"):
         print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")
 
 

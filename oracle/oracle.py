@@ -166,3 +166,15 @@ def mean_iou(conf):
     tp = np.diag(conf)
     with np.errstate(divide="ignore", invalid="ignore"):
         return float(np.nanmean(tp / (conf.sum(0) + conf.sum(1) - tp)))
+
+
+def kd_loss_multi(s, teachers, weights, T=1.0, need_grad=True):
+    """KD term of trainer/ensemble_trainer.py:76-83: sum_k weights[k] * KLDivergenceLoss(T)(s, teachers[k]) and its
+    gradient, as the weighted sum of the single-teacher oracle (losses/KLDiv.py:19-23)."""
+    loss, ds = 0.0, (np.zeros_like(_c(s)) if need_grad else None)
+    for t, w in zip(teachers, weights):
+        l, g = kd_loss(s, t, T, False, need_grad)
+        loss += float(w) * l
+        if need_grad:
+            ds += np.float32(w) * g
+    return loss, ds

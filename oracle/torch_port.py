@@ -71,3 +71,11 @@ def layerwise_step(sites, logits_s, logits_t, kd_temperature=1.0, hint_num_class
         kd = kl_div_loss(logits_s, logits_t, kd_temperature)
     hint.backward()
     return float(hint), float(kd)
+
+
+def ensemble_kd_loss(output_st, ensemble_outputs, output_tc, temperature=1.0, weight=1.0, accumulation_steps=1):
+    """trainer/ensemble_trainer.py:81-83: kd_loss over the ensemble members and the own teacher."""
+    from functools import reduce
+    kd = reduce(lambda acc, elem: acc + weight * kl_div_loss(output_st, elem, temperature), ensemble_outputs, 0)
+    kd = kd + kl_div_loss(output_st, output_tc, temperature)
+    return kd / (weight * len(ensemble_outputs) + 1) / accumulation_steps
