@@ -25,11 +25,13 @@ PLAN_CIFAR_RESNET44 = [(64, 64)] * 8                                           #
 class EventLog:
     """CUDA-event timeline on the launching stream: one event after every kernel call."""
 
-    def __init__(self):
-        self.names, self.events = [], []
+    def __init__(self, external=False):
+        # external=True: events that may be recorded inside a CUDA-graph capture (they become event-record nodes and
+        # are re-recorded by every replay, so the log then holds the timeline of the LAST replay)
+        self.names, self.events, self.external = [], [], external
 
     def mark(self, name):
-        ev = torch.cuda.Event(enable_timing=True)
+        ev = torch.cuda.Event(enable_timing=True, external=True) if self.external else torch.cuda.Event(enable_timing=True)
         ev.record(torch.cuda.current_stream())
         self.names.append(name)
         self.events.append(ev)
@@ -177,6 +179,19 @@ class HotPathStep:
             launches += 2
         self.launches_per_step = launches
         return self.hint_losses.sum(), self.kd_loss
+
+    def capture(self, xs, teacher_feats, logits_s=None, logits_t=None, log=None):
+        """Capture one pass (every libkdcc launch of `step`) into a CUDA graph.  Returns (graph, (hint_sum, kd)); the
+        result tensors are rewritten by every `graph.replay()`.  `log` must be an EventLog(external=True)."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # one un-captured pass: function attributes / lazy module loads happen here
+            self.step(xs, teacher_feats, logits_s, logits_t)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.step(xs, teacher_feats, logits_s, logits_t, log=log)
+        return graph, out
 
     # ---- algorithmic work per step (SURVEY.md 8d), used for the roofline figures -----------------------------
     def algorithmic(self):
