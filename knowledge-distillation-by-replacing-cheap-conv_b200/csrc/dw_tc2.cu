@@ -93,6 +93,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();  // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -316,7 +317,7 @@ static int conv2_launch(const void *in, C2Params p, cudaStream_t st) {
     attr_smem = smem;
   }
   const int grid = (int)min(p.pairs, (long)kNumSMs);
-  dw_tc_conv2_kernel<D><<<grid, C2_THREADS, smem, st>>>(tm, tm_out, p);
+  launch_pdl(dw_tc_conv2_kernel<D>, dim3(grid), dim3(C2_THREADS), (size_t)smem, st, tm, tm_out, p);
   return launch_status();
 }
 

@@ -88,6 +88,7 @@ dw_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();  // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -270,6 +271,7 @@ static int w2_splits(int N, int C) { return tc_unit_splits(C, (N + 1) / 2); }
 size_t dw_tc_wgrad2_workspace(int N, int C, int k) { return (size_t)w2_splits(N, C) * C * k * k * sizeof(float) + 16; }
 
 __global__ void dw_tc_wgrad2_reduce_kernel(const float *__restrict__ part, float *__restrict__ dw, int splits, long count) {
+  pdl_prologue_done();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   float acc = 0.f;
@@ -296,11 +298,11 @@ static int wgrad2_launch(const void *x, const void *dy, float *dw, float *part, 
     attr_done = 1;
   }
   const int grid = (int)min(p.units, (long)kNumSMs);
-  dw_tc_wgrad2_kernel<K><<<grid, W2_THREADS, smem, st>>>(tm_x, tm_dy, p);
+  launch_pdl(dw_tc_wgrad2_kernel<K>, dim3(grid), dim3(W2_THREADS), (size_t)smem, st, tm_x, tm_dy, p);
   rc = launch_status();
   if (rc || p.splits == 1) return rc;
   const long count = (long)p.C * K * K;
-  dw_tc_wgrad2_reduce_kernel<<<(unsigned)ceil_div<long>(count, 256), 256, 0, st>>>(part, dw, p.splits, count);
+  launch_pdl(dw_tc_wgrad2_reduce_kernel, dim3((unsigned)ceil_div<long>(count, 256)), dim3(256), 0, st, part, dw, p.splits, count);
   return launch_status();
 }
 

@@ -17,6 +17,33 @@ static inline int launch_status() {
   return e == cudaSuccess ? KDCC_OK : (int)e;
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// Kernels launched through launch_pdl may become resident while their predecessor in the stream is still running:
+// their prologue (shared-memory fills, barrier init, TMEM allocation, descriptor prefetch) overlaps its tail.  Every
+// such kernel calls pdl_prologue_done() before its first global-memory access: it lets ITS dependents start early and
+// then waits until the predecessor grid has completed and flushed.  KDCC_NO_PDL=1 restores plain stream order.
+__device__ __forceinline__ void pdl_prologue_done() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+bool pdl_enabled();  // api_misc.cu
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>

@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(kLossThreads) kd_loss_generic_kernel(const KdP
 __global__ void __launch_bounds__(256) loss_finalize_kernel(const float *__restrict__ partials, int count,
                                                             double coef, float *__restrict__ out) {
   __shared__ double sh[256];
+  pdl_prologue_done();
   double acc = 0.0;
   for (int i = threadIdx.x; i < count; i += 256) acc += (double)partials[i];
   sh[threadIdx.x] = acc;
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(kLossThreads) hint_loss_kernel(const HintParam
   using V = Vec16<T>;
   constexpr int VN = V::N;
   __shared__ float scratch[32];
+  pdl_prologue_done();
   const char *__restrict__ sb = static_cast<const char *>(p.s);
   const char *__restrict__ tb = static_cast<const char *>(p.t);
   char *__restrict__ db = static_cast<char *>(p.ds);
@@ -436,6 +438,7 @@ __global__ void __launch_bounds__(kLossThreads) hint_loss_scalar_kernel(const Hi
 // small utilities
 // ------------------------------------------------------------------------------------------------
 __global__ void cast_f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long n) {
+  pdl_prologue_done();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
 }
@@ -538,7 +541,7 @@ KDCC_API int kdcc_kd_loss(const void *s, const void *t, void *ds, float *loss_ou
   int rc = launch_status();
   if (rc) return rc;
   const double coef = (double)kLn2 * (double)T * (double)T / ((double)N * (double)HW);
-  loss_finalize_kernel<<<1, 256, 0, st>>>(p.partials, used, coef, loss_out);
+  launch_pdl(loss_finalize_kernel, dim3(1), dim3(256), 0, st, p.partials, used, coef, loss_out);
   return launch_status();
 }
 
@@ -594,7 +597,7 @@ KDCC_API int kdcc_kd_loss_multi(const void *s, const void *const *teachers, cons
   int rc = launch_status();
   if (rc) return rc;
   const double coef = (double)kLn2 * (double)T * (double)T / ((double)N * (double)HW);
-  loss_finalize_kernel<<<1, 256, 0, st>>>(p.partials, grid, coef, loss_out);
+  launch_pdl(loss_finalize_kernel, dim3(1), dim3(256), 0, st, p.partials, grid, coef, loss_out);
   return launch_status();
 }
 
@@ -604,8 +607,8 @@ static int launch_hint(const HintParams &p, bool vectorised, cudaStream_t st) {
   if (vectorised) {
     const long nvec = p.total / V::N;
     const int grid = (int)min((long)kMaxLossBlocks, ceil_div<long>(nvec, (long)kLossThreads * 4));
-    if (p.coef) hint_loss_kernel<T, true, 4><<<grid, kLossThreads, 0, st>>>(p);
-    else hint_loss_kernel<T, false, 4><<<grid, kLossThreads, 0, st>>>(p);
+    if (p.coef) launch_pdl(hint_loss_kernel<T, true, 4>, dim3(grid), dim3(kLossThreads), 0, st, p);
+    else launch_pdl(hint_loss_kernel<T, false, 4>, dim3(grid), dim3(kLossThreads), 0, st, p);
     return grid;
   }
   const int grid = (int)min((long)kMaxLossBlocks, ceil_div<long>(p.total, kLossThreads));
@@ -646,7 +649,7 @@ KDCC_API int kdcc_hint_loss(const void *s, const void *t, const float *w, int w_
   else used = launch_hint<__nv_bfloat16>(p, vectorised, st);
   int rc = launch_status();
   if (rc) return rc;
-  loss_finalize_kernel<<<1, 256, 0, st>>>(p.partials, used, 1.0, loss_out);
+  launch_pdl(loss_finalize_kernel, dim3(1), dim3(256), 0, st, p.partials, used, 1.0, loss_out);
   return launch_status();
 }
 
@@ -654,7 +657,7 @@ KDCC_API int kdcc_cast_f32_to_bf16(const float *src, void *dst, long n, kdcc_str
   if (!src || !dst || n < 0) return KDCC_EINVAL;
   if (n == 0) return KDCC_OK;
   const int grid = (int)min((long)kNumSMs * 8, ceil_div<long>(n, 256));
-  cast_f32_to_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16 *>(dst), n);
+  launch_pdl(cast_f32_to_bf16_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), src, static_cast<__nv_bfloat16 *>(dst), n);
   return launch_status();
 }
 

@@ -112,6 +112,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue_done();  // the prologue overlapped the previous kernel's tail; global memory from here on
 
   const int out_batches = p.r_spans_batch ? 1 : p.batch;
   const long items = (long)p.tiles_i * p.tiles_j * p.splits * out_batches;
@@ -305,6 +306,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
 // out[i] = sum_s part[s][i]   (fixed order)
 __global__ void reduce_splits_kernel(const float *__restrict__ part, float *__restrict__ out, int splits, long count) {
+  pdl_prologue_done();
   const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= count) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -363,7 +365,7 @@ static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaS
   }
   const long items = (long)p.tiles_i * p.tiles_j * p.splits * (p.r_spans_batch ? 1 : p.batch);
   const int grid = (int)min(items, (long)kNumSMs);
-  pw_gemm_sm100_kernel<BJ, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(tm_a, tm_b, tm_out, p);
+  launch_pdl(pw_gemm_sm100_kernel<BJ, A_MN, B_MN>, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM, st, tm_a, tm_b, tm_out, p);
   return launch_status();
 }
 
@@ -451,7 +453,7 @@ int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long 
   }
   if (rc || p.splits == 1) return rc;
   const long count = (long)Nc * K;  // multiple of 4 because K % 8 == 0
-  reduce_splits_kernel<<<(unsigned)ceil_div<long>(count / 4, 256), 256, 0, st>>>(part, dw, p.splits, count);
+  launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div<long>(count / 4, 256)), dim3(256), 0, st, part, dw, p.splits, count);
   return launch_status();
 }
 
