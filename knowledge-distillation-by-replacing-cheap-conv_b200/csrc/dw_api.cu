@@ -44,6 +44,8 @@ KDCC_API int kdcc_dw_fwd(const void *x, const float *w, const float *bias, void 
   if (!aligned16(x) || !aligned16(y)) return KDCC_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (layout == KDCC_LAYOUT_NCHW) return dw_tc_conv(x, w, bias, y, N, C, H, W, Ho, Wo, k, dil, pad, 0, st);
+  if (dtype == KDCC_BF16 && dw_nhwc3_supported(C, k, dil, pad) && !env_flag("KDCC_DW_FORCE_DIRECT"))
+    return dw_nhwc3_conv(x, w, bias, y, N, H, W, C, 0, st);
   if (use_tma(C, k, dil, dtype)) return dw_tma_conv(x, w, bias, y, N, H, W, C, Ho, Wo, k, dil, pad, 0, st);
   if (dtype == KDCC_F32) return dw_direct_fwd<float>(x, w, bias, y, N, H, W, C, Ho, Wo, k, dil, pad, 0, st);
   return dw_direct_fwd<__nv_bfloat16>(x, w, bias, y, N, H, W, C, Ho, Wo, k, dil, pad, 0, st);
@@ -62,6 +64,10 @@ KDCC_API size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, i
   if (dtype == KDCC_BF16 && dw_tma_supported(C, k, dil)) {
     const size_t s2 = (size_t)dw_tma_wgrad_splits(N, Ho, Wo, C, k, dil);
     if (s2 > splits) splits = s2;
+  }
+  if (dtype == KDCC_BF16 && dw_nhwc3_supported(C, k, dil, pad)) {
+    const size_t s3 = (size_t)dw_nhwc3_wgrad_ctas(N, H, W, C);
+    if (s3 > splits) splits = s3;
   }
   return splits * (size_t)(k * k + 1) * (size_t)C * sizeof(float);
 }
@@ -95,6 +101,16 @@ KDCC_API int kdcc_dw_bwd(const void *x, const float *w, const void *dy, void *dx
     return KDCC_OK;
   }
   const bool tma = use_tma(C, k, dil, dtype);
+  const bool n3 = dtype == KDCC_BF16 && dw_nhwc3_supported(C, k, dil, pad) && !env_flag("KDCC_DW_FORCE_DIRECT");
+  if (n3) {  // streaming 3 x 3 kernels: dX is the conv over dy with mirrored taps (pad' = 1), dW its own kernel
+    if (dx) {
+      rc = dw_nhwc3_conv(dy, w, nullptr, dx, N, H, W, C, 1, st);
+      if (rc) return rc;
+    }
+    if (dw && !dbias) return dw_nhwc3_wgrad(x, dy, dw, static_cast<float *>(workspace), N, H, W, C, st);
+    if (!dw && !dbias) return KDCC_OK;
+    dx = nullptr;  // bias gradient requested: the direct weight-gradient kernel produces dw and dbias together
+  }
   if (dx) {
     if (tma && padt >= 0) rc = dw_tma_conv(dy, w, nullptr, dx, N, Ho, Wo, C, H, W, k, dil, padt, 1, st);
     else if (dtype == KDCC_F32) rc = dw_direct_fwd<float>(dy, w, nullptr, dx, N, Ho, Wo, C, H, W, k, dil, padt, 1, st);

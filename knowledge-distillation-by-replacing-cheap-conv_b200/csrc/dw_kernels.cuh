@@ -26,6 +26,13 @@ int dw_tma_wgrad_splits(int N, int Ho, int Wo, int C, int k, int dil);
 int dw_tma_wgrad(const void *x, const void *dy, float *dw, float *part, int N, int H, int W, int C, int Ho, int Wo,
                  int k, int dil, int pad, cudaStream_t st);
 
+// ---- streaming 3 x 3 (dil 1, pad 1) NHWC bf16 kernels: dw_nhwc3.cu ------------------------------------
+bool dw_nhwc3_supported(int C, int k, int dil, int pad);
+int dw_nhwc3_conv(const void *in, const float *w, const float *bias, void *out, int N, int H, int W, int C, int flip,
+                  cudaStream_t st);
+int dw_nhwc3_wgrad_ctas(int N, int H, int W, int C);
+int dw_nhwc3_wgrad(const void *x, const void *dy, float *dw, float *part, int N, int H, int W, int C, cudaStream_t st);
+
 // ---- tensor-core (tcgen05) bf16 kernels on NCHW planes: dw_tc.cu, dw_tc_wgrad.cu ---------------------
 bool dw_tc_supported(int Hi, int Wi, int Ho, int Wo, int k, int dil);
 int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int N, int C, int Hi, int Wi, int Ho,

@@ -69,11 +69,15 @@ def test_block_fp32_matches_reference_golden(kdcc, golden_block, tag):
         assert relerr(mine, g[f"{tag}/{name}"]) < TOL[torch.float32], name
 
 
-@pytest.mark.parametrize("mode", ["tma", "tma_plain_load", "tma_plain_store", "direct"])
+@pytest.mark.parametrize("mode", ["default", "tma", "tma_plain_load", "tma_plain_store", "direct"])
 @pytest.mark.parametrize("tag", BLOCK_CASES)
 def test_block_bf16_matches_reference_golden(kdcc, golden_block, tag, mode, monkeypatch):
-    monkeypatch.setenv("KDCC_DW_MODE", {"tma": "0", "tma_plain_load": "1", "tma_plain_store": "2", "direct": "0"}[mode])
+    # "default": what the dispatcher picks (streaming 3x3 kernels for k=3 d=1 p=1, TMA-staged kernels for k=9);
+    # the tma* modes switch the streaming 3x3 kernels off so that the TMA-staged k=3 configuration stays covered
+    monkeypatch.setenv("KDCC_DW_MODE", {"tma_plain_load": "1", "tma_plain_store": "2"}.get(mode, "0"))
     monkeypatch.setenv("KDCC_DW_FORCE_DIRECT", "1" if mode == "direct" else "0")
+    if mode.startswith("tma"):
+        monkeypatch.setenv("KDCC_DW_NHWC3_OFF", "1")
     g = golden_block
     N, Ci, Co, H, W, k, d, p = [int(v) for v in g[f"{tag}/geom"]]
     y, dx, dwd, dwp = run_block(kdcc, g[f"{tag}/x"], g[f"{tag}/w_dw"], g[f"{tag}/w_pw"], g[f"{tag}/dy"], k, d, p,
@@ -119,6 +123,36 @@ def test_block_matches_oracle_seeded(kdcc, geom, dtype):
     ry, rdx, rdwd, rdwp = oracle_block(x, w_dw, w_pw, dy, k, d, p, dtype)
     for name, mine, ref in (("y", y, ry), ("dx", dx, rdx), ("dw_dw", dwd, rdwd), ("dw_pw", dwp, rdwp)):
         assert relerr(mine, ref) < TOL[dtype], name
+
+
+SEEDED_NHWC3 = [
+    # N,  C,   H,   W      (k=3, d=1, p=1, channels_last bf16 -> dw_nhwc3.cu)
+    (3, 64, 8, 8),          # CIFAR ResNet44 layer3 shape: 8 vectors per pixel, 4 columns per warp
+    (2, 16, 5, 7),          # two vectors per pixel: a warp spans 16 columns, ragged
+    (2, 8, 5, 7),           # one vector per pixel: not streamed (falls to the TMA-staged / direct kernels)
+    (1, 256, 33, 19),       # exactly one warp of vectors, rows not a multiple of the 32-row tile
+    (2, 512, 40, 24),       # two channel groups
+    (1, 128, 70, 130),      # 16 vectors per pixel, more than one tile in both directions
+]
+
+
+@pytest.mark.parametrize("geom", SEEDED_NHWC3)
+def test_depthwise_nhwc3_streaming_matches_oracle(kdcc, geom):
+    from oracle import oracle as orc
+    N, C, H, W = geom
+    rs = np.random.RandomState(77 + C + W)
+    x = q(rs.standard_normal((N, C, H, W)).astype(np.float32), torch.bfloat16)
+    w = (rs.uniform(-1, 1, (C, 1, 3, 3)) / 3).astype(np.float32)
+    dy = q(rs.standard_normal((N, C, H, W)).astype(np.float32), torch.bfloat16)
+    xt = torch.from_numpy(x).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wt = torch.from_numpy(w).cuda().requires_grad_(True)
+    y = kdcc.functional.depthwise_conv(xt, wt, None, 3, 1, 1)
+    y.backward(torch.from_numpy(dy).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    ry = orc.dw_fwd(x, w, 3, 1, 1)
+    rdx, rdw, _ = orc.dw_bwd(x, w, dy, 3, 1, 1)
+    assert relerr(y.detach().float().cpu().numpy(), ry) < TOL[torch.bfloat16]
+    assert relerr(xt.grad.float().cpu().numpy(), rdx) < TOL[torch.bfloat16]
+    assert relerr(wt.grad.cpu().numpy(), rdw) < 1e-4   # fp32 accumulation of exact bf16 products
 
 
 SEEDED_NCHW = [
