@@ -12,10 +12,11 @@ namespace kdcc {
 
 constexpr int CONF_THREADS = 256;
 constexpr int CONF_MAX_C = 32;
+constexpr int CONF_OCC = 6;  // CTAs per SM: the grid-stride grid is exactly one resident wave
 
 // logits (n, c, q) at s + n*batch_stride + c*class_stride + q (pixel stride 1: NCHW); labels int64 [N][HW]
 template <typename T, int VEC>
-__global__ void __launch_bounds__(CONF_THREADS)
+__global__ void __launch_bounds__(CONF_THREADS, CONF_OCC)
 confusion_kernel(const T *__restrict__ s, const long long *__restrict__ labels, unsigned long long *__restrict__ conf,
                  int N, int C, long HW, long batch_stride, long class_stride, int ignore_index) {
   extern __shared__ unsigned int hist[];  // [warps][C*C] per-warp counts (<= 32 KB)
@@ -80,7 +81,7 @@ KDCC_API int kdcc_confusion_update(const void *logits, const long long *labels, 
   auto *out = reinterpret_cast<unsigned long long *>(conf);
   const bool vec4 = dtype == KDCC_F32 && HW % 4 == 0 && batch_stride % 4 == 0 && class_stride % 4 == 0 && aligned16(logits);
   const long groups = (long)N * (vec4 ? HW / 4 : HW);
-  const int grid = (int)min((long)kNumSMs * 8, ceil_div<long>(groups, CONF_THREADS));
+  const int grid = (int)min((long)kNumSMs * CONF_OCC, ceil_div<long>(groups, CONF_THREADS));
   if (vec4)
     confusion_kernel<float, 4><<<grid, CONF_THREADS, dyn, st>>>(static_cast<const float *>(logits), labels, out, N, C, HW,
                                                                 batch_stride, class_stride, ignore_index);
