@@ -96,7 +96,9 @@ class HotPathStep:
         self.dx = e(cmax, height, width) if need_dx else None
         self.y = e(omax, self.Ho, self.Wo)
         self.dy = e(omax, self.Ho, self.Wo)
-        self.w_pw_lp = torch.empty(max(co * ci for ci, co in self.plan), dtype=dtype, device=self.device)
+        # bf16 copy of the WHOLE flat parameter bucket, refreshed by one cast launch per step (the pointwise GEMMs read
+        # their weights from it; one launch instead of one per site)
+        self.flat_lp = torch.empty(total, dtype=dtype, device=self.device)
         ws_bytes = self.L.kdcc_loss_workspace_bytes()
         for ci, co in self.plan:
             M = n * self.Ho * self.Wo
@@ -142,16 +144,18 @@ class HotPathStep:
         mark = log.mark if log is not None else (lambda name: None)
         launches = 0
         mark("begin")
+        if code == _abi.BF16:
+            chk(L.kdcc_cast_f32_to_bf16(_ptr(self.flat_params), _ptr(self.flat_lp), self.flat_params.numel(), st), "cast")
+            mark("cast_w")
+            launches += 1
         for i, (ci, co) in enumerate(self.plan):
             w_dw, w_pw, g_dw, g_pw = self._site_weights(i)
             x, tf = xs[i], teacher_feats[i]
             M = n * Ho * Wo
             w_lp = w_pw
             if code == _abi.BF16:
-                w_lp = self.w_pw_lp[:co * ci]
-                chk(L.kdcc_cast_f32_to_bf16(_ptr(w_pw), _ptr(w_lp), co * ci, st), "cast")
-                mark("cast_w")
-                launches += 1
+                a_, b_, c_ = self._views[i]
+                w_lp = self.flat_lp[b_:c_]
             chk(L.kdcc_dw_fwd(_ptr(x), _ptr(w_dw), None, _ptr(self.mid), n, H, W, ci, k, d, p, lay, code, st), "dw_fwd")
             mark("dw_fwd")
             chk(L.kdcc_pw_fwd(_ptr(self.mid), _ptr(w_lp), None, None, 0, _ptr(self.y), None, M, ci, co, n, lay, code, st), "pw_fwd")

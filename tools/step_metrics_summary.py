@@ -30,10 +30,8 @@ order = list(launch.values())
 conv_seen = gemm_seen = 0
 for e in order:
     n = e["name"]
-    if n == "cast_f32_to_bf16_kernel":
-        conv_seen = gemm_seen = 0
-    if n == "dw_tc_conv2_kernel":
-        e["fam"] = "dw_fwd" if conv_seen == 0 else "dw_bwd(dX)"
+    if n == "dw_tc_conv2_kernel":  # per site: forward conv, ..., input-gradient conv
+        e["fam"] = "dw_fwd" if conv_seen % 2 == 0 else "dw_bwd(dX)"
         conv_seen += 1
     elif n == "pw_gemm_sm100_kernel":
         e["fam"] = ("pw_fwd", "pw_bwd_dw", "pw_bwd_dx")[gemm_seen % 3]
