@@ -165,6 +165,10 @@ SEEDED_NCHW = [
     (1, 16, 16, 16, 24, 7, 1, 3),       # 7x7
     (2, 8, 16, 20, 24, 5, 2, 0),        # no padding: output (12 x 16) smaller than input
     (1, 512, 512, 128, 128, 9, 5, 20),  # one full-size 51M-plan site
+    (3, 24, 8, 37, 40, 9, 5, 20),       # odd batch (weight-gradient image pairs: 2 + 1), ragged rows
+    (5, 8, 8, 16, 32, 5, 1, 2),         # undilated 5x5: a single phase exactly 32 columns wide
+    (1, 8, 8, 128, 128, 3, 1, 1),       # 3x3 on a full plane: tiled Toeplitz conv + whole-plane weight gradient
+    (2, 16, 8, 64, 64, 3, 2, 2),        # dilation 2, two phases of 32 columns
 ]
 
 
