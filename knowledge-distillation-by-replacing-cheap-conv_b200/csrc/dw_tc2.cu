@@ -29,14 +29,17 @@ namespace kdcc {
 
 constexpr int C2_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 regroup + Toeplitz, warps 6-9 epilogue
 constexpr int C2_STG = 2 * 128 * 128;  // one landed plane: two boxes of 128 rows x 128 bytes
-constexpr int C2_TZ = 2048;            // one Toeplitz tile: [4 K chunks][32 columns][16 bytes]
+constexpr int C2_TZ_CHUNK = 512;       // one Toeplitz K chunk: [32 output columns][16 bytes]
 constexpr int C2_MAXROWS = 128 + 48;   // operand rows: plane + halo
 
 struct C2Params {
   int N, C, H, W, k, dil, pad, flip;
   int rows_p;     // 128 + dil*(k-1): rows of the phase-major operand
-  int ks;         // K slices of 16 phase-columns in use (1 or 2)
+  int ks;         // K slices of 16 phase-columns per N-tile
   int qoff;       // pad / dil
+  int nt;         // N-tiles (32 output phase-columns) per phase: 1 when a phase is at most 32 columns wide
+  int zpad;       // nt > 1: always-zero K chunks in front of chunk 0 (the first tile's window starts at 8*floor(-qoff/8))
+  int chunks_p;   // K chunk slots per phase of the operand
   int planes, splits;
   long pairs;
   const float *w, *bias;
@@ -44,18 +47,22 @@ struct C2Params {
   int dbg;  // KDCC_TC_DEBUG (timing experiments only): 1 skip Toeplitz rebuild, 2 skip MMAs, 4 skip stores, 8 skip regrouping
 };
 
-template <int D>
+// NT / KS: N-tiles per phase and K slices per N-tile known at compile time (0 = read them from the parameters): the
+// single issuing thread then runs a straight line of MMAs, one integer add per operand each.
+template <int D, int NT, int KS>
 __global__ void __launch_bounds__(C2_THREADS, 1)
 dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, const C2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const uint32_t lbo = (uint32_t)p.rows_p * 16u;       // bytes between K chunks of the operand
-  const uint32_t xp_bytes = (uint32_t)D * 4u * lbo;    // one operand buffer
+  const uint32_t xp_bytes = (uint32_t)(D * p.chunks_p) * lbo;  // one operand buffer
   const uint32_t xp_off = 2 * C2_STG;
   const uint32_t tz_off = xp_off + 2 * xp_bytes;
-  const uint32_t tz_bytes = (uint32_t)p.k * C2_TZ;
-  constexpr uint32_t OB = 32 * 16 * D;                 // one epilogue staging tile: 32 rows x 8*D bf16 columns
+  const uint32_t tz_u = (uint32_t)(2 * p.ks) * C2_TZ_CHUNK;  // one tap row's Toeplitz tile: [2*ks K chunks][32][16 B]
+  const uint32_t tz_bytes = (uint32_t)p.k * tz_u;
+  constexpr int G = D == 1 ? 4 : (D == 2 ? 2 : 1);      // column groups per store tile
+  constexpr uint32_t OB = 32 * 16 * D * G;             // one epilogue staging tile: 32 rows x 8*D*G bf16 columns
   const uint32_t ob_off = (tz_off + 2 * tz_bytes + 127u) & ~127u;
   const uint32_t bar_off = ob_off + 4 * 2 * OB;
   const uint32_t bar_base = smem_base + bar_off;
@@ -114,11 +121,11 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       constexpr uint32_t hi = (128u >> 4) | (1u << 14);  // 8-row groups 128 B apart, descriptor version 1, no swizzle
       const uint32_t a_lbo = (lbo >> 4) << 16;
       constexpr uint32_t b_lbo = (512u >> 4) << 16;      // Toeplitz K chunks: 32 columns x 16 B apart
-      uint32_t a_off[D][2];
+      const uint32_t chunk16 = lbo >> 4;  // one K chunk of the operand, in descriptor units
+      uint32_t a_phase[D];                // operand offset of every phase: the issue loop below only adds
 #pragma unroll
-      for (int b = 0; b < D; ++b)
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) a_off[b][kk] = ((uint32_t)(b * 4 + kk * 2) * lbo) >> 4;
+      for (int b = 0; b < D; ++b) a_phase[b] = (uint32_t)(b * p.chunks_p) * chunk16;
+      const uint32_t a_tile = 4u * chunk16, a_slice = 2u * chunk16;
       int it = 0, unit = -1;
       for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
         const int s = it & 1;
@@ -137,11 +144,21 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 #pragma unroll 1
           for (int u = 0; u < p.k; ++u) {
             const uint32_t a_u = a_base + (uint32_t)(u * p.dil);       // tap row u: u*d rows of 16 bytes further down
-            const uint32_t b_u = b_base + (uint32_t)u * (C2_TZ >> 4);
+            const uint32_t b_u = b_base + (uint32_t)u * (tz_u >> 4);
+            const int nt = NT ? NT : p.nt, ks = KS ? KS : p.ks;
 #pragma unroll
             for (int b = 0; b < D; ++b) {
-              ptx::umma_f16_ss(d0 + b * 32, a_u + a_off[b][0], hi, b_u, hi, idesc, u ? 1u : 0u);
-              if (p.ks > 1) ptx::umma_f16_ss(d0 + b * 32, a_u + a_off[b][1], hi, b_u + (1024u >> 4), hi, idesc, 1u);
+              // N-tile t of phase b: its K window starts at chunk slot 4t (the zero chunks in front make that uniform)
+              uint32_t a_t = a_u + a_phase[b];
+              uint32_t d_t = d0 + (uint32_t)(b * nt) * 32u;
+#pragma unroll
+              for (int t = 0; t < nt; ++t, a_t += a_tile, d_t += 32u) {
+                ptx::umma_f16_ss(d_t, a_t, hi, b_u, hi, idesc, u ? 1u : 0u);
+                uint32_t a_s = a_t + a_slice, b_s = b_u + (1024u >> 4);
+#pragma unroll
+                for (int ss = 1; ss < ks; ++ss, a_s += a_slice, b_s += (1024u >> 4))
+                  ptx::umma_f16_ss(d_t, a_s, hi, b_s, hi, idesc, 1u);
+              }
             }
           }
         }
@@ -165,9 +182,9 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         for (int v = 0; v < 9; ++v) wv[v] = v < p.k ? __ldg(wr + (p.flip ? p.k - 1 - v : v)) : 0.f;
 #pragma unroll
         for (int v = 0; v < 9; ++v) {
-          const int qp = q - p.qoff + v;
-          if (v < p.k && qp >= 0 && qp < 32)
-            *reinterpret_cast<__nv_bfloat16 *>(ts + u * C2_TZ + (qp >> 3) * 512 + q * 16 + (qp & 7) * 2) = __float2bfloat16_rn(wv[v]);
+          const int qp = q - p.qoff + v + 8 * p.zpad;  // reduction index inside the N-tile's K window
+          if (v < p.k && qp >= 0 && qp < 16 * p.ks)
+            *reinterpret_cast<__nv_bfloat16 *>(ts + u * tz_u + (qp >> 3) * C2_TZ_CHUNK + q * 16 + (qp & 7) * 2) = __float2bfloat16_rn(wv[v]);
         }
       }
       ptx::fence_proxy_async_smem();
@@ -220,7 +237,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
               const uint32_t sel = ((x0 & 1) ? 0x32u : 0x10u) | ((x1 & 1) ? 0x7600u : 0x5400u);
               o[m] = __byte_perm(in[x0 >> 1], in[x1 >> 1], sel);
             }
-            *reinterpret_cast<uint4 *>(xp + (size_t)(b * 4 + g) * lbo) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4 *>(xp + (size_t)(b * p.chunks_p + p.zpad + g) * lbo) = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
       }
@@ -245,31 +262,37 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       const int c = w.channel();
       const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
       const uint32_t t_row = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
+      // a store tile = G groups of 8*D output columns (G chosen so that a tile row is 64-128 bytes)
 #pragma unroll 1
-      for (int g = 0; g * D < nchunks; ++g, ++gi) {
-        uint32_t v[D][8];
-#pragma unroll
-        for (int b = 0; b < D; ++b) ptx::tmem_ld_32x32b_x8(t_row + b * 32 + g * 8, v[b]);
-        ptx::tmem_ld_wait();
-        if (gi >= 2) {  // the store that read this staging tile two groups ago has finished reading it
+      for (int g0 = 0; g0 * D < nchunks; g0 += G, ++gi) {
+        if (gi >= 2) {  // the store that read this staging tile two tiles ago has finished reading it
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
         }
         const uint32_t tile = ob + (uint32_t)(gi & 1) * OB;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-          uint32_t o[4];
+        for (int gg = 0; gg < G; ++gg) {
+          const int g = g0 + gg;
+          if (g * D >= nchunks) break;
+          uint32_t v[D][8];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int x0 = 8 * j + 2 * m, x1 = x0 + 1;  // output columns of the group: column x = phase x % D, index x / D
-            o[m] = pack_bf16x2(__uint_as_float(v[x0 % D][x0 / D]) + bias, __uint_as_float(v[x1 % D][x1 / D]) + bias);
+          for (int b = 0; b < D; ++b) ptx::tmem_ld_32x32b_x8(t_row + (uint32_t)((b * p.nt + (g >> 2)) * 32 + (g & 3) * 8), v[b]);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            uint32_t o[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int x0 = 8 * j + 2 * m, x1 = x0 + 1;  // output columns of the group: column x = phase x % D, index x / D
+              o[m] = pack_bf16x2(__uint_as_float(v[x0 % D][x0 / D]) + bias, __uint_as_float(v[x1 % D][x1 / D]) + bias);
+            }
+            *reinterpret_cast<uint4 *>(smem_gen + tile + lane * (16 * D * G) + 16 * (gg * D + j)) = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          *reinterpret_cast<uint4 *>(smem_gen + tile + lane * (16 * D) + 16 * j) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.dbg & 4)) {
-          ptx::tma_store_4d(&tm_out, smem_base + tile, 8 * D * g, 32 * quad, c, w.pl);
+          ptx::tma_store_4d(&tm_out, smem_base + tile, 8 * D * g0, 32 * quad, c, w.pl);
           ptx::tma_store_commit();
         }
       }
@@ -294,10 +317,18 @@ bool dw_tc_conv2_supported(int Hi, int Wi, int Ho, int Wo, int k, int dil, int p
   if (Hi != Ho || Wi != Wo || Hi > 128 || Wi > 128 || Wi % 8 != 0) return false;
   if (k % 2 == 0 || k > 9 || halo > 48 || 2 * pad != halo || pad % dil != 0) return false;
   if (dil != 1 && dil != 2 && dil != 5) return false;   // instantiated phase counts
-  return (Wi + dil - 1) / dil <= 32;                     // one phase fits the 32-wide reduction
+  const int nt = ((Wi + dil - 1) / dil + 31) / 32;       // N-tiles per phase: the d accumulators of a plane must fit 256 TMEM columns
+  if (dil * nt * 32 > 256) return false;
+  if (nt > 1) {                                          // operand with zero chunks around every phase: must fit shared memory twice
+    const int qoff = pad / dil, zpad = (qoff + 7) / 8;
+    const int ks = ((31 + k - 1 - qoff + 8 * zpad) / 8 + 2) / 2;
+    const int chunks_p = 4 * (nt - 1) + 2 * ks;
+    if (2 * C2_STG + 2 * dil * chunks_p * (128 + halo) * 16 + 2 * k * 2 * ks * C2_TZ_CHUNK + 8 * 32 * 16 * dil * (dil == 1 ? 4 : (dil == 2 ? 2 : 1)) + 2048 > 227 * 1024) return false;
+  }
+  return true;
 }
 
-template <int D>
+template <int D, int NT, int KS>
 static int conv2_launch(const void *in, C2Params p, cudaStream_t st) {
   CUtensorMap tm;
   const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.C, (uint64_t)p.N};
@@ -306,18 +337,19 @@ static int conv2_launch(const void *in, C2Params p, cudaStream_t st) {
   int rc = make_tmap_bf16(&tm, in, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   CUtensorMap tm_out;
-  const uint32_t obox[4] = {8 * D, 32, 1, 1};
+  const uint32_t obox[4] = {8 * D * (D == 1 ? 4 : (D == 2 ? 2 : 1)), 32, 1, 1};
   rc = make_tmap_bf16(&tm_out, p.out, 4, dims, strides, obox, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  const int smem = 2 * C2_STG + 2 * D * 4 * p.rows_p * 16 + 2 * p.k * C2_TZ + 128 + 8 * 32 * 16 * D + 256 + 1024;
+  const int smem = 2 * C2_STG + 2 * D * p.chunks_p * p.rows_p * 16 + 2 * p.k * 2 * p.ks * C2_TZ_CHUNK + 128 + 8 * 32 * 16 * D * (D == 1 ? 4 : (D == 2 ? 2 : 1)) + 256 + 1024;
+  if (smem > 227 * 1024 || D * p.nt * 32 > 256) return KDCC_ESHAPE;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tc_conv2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(dw_tc_conv2_kernel<D, NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     attr_smem = smem;
   }
   const int grid = (int)min(p.pairs, (long)kNumSMs);
-  launch_pdl(dw_tc_conv2_kernel<D>, dim3(grid), dim3(C2_THREADS), (size_t)smem, st, tm, tm_out, p);
+  launch_pdl(dw_tc_conv2_kernel<D, NT, KS>, dim3(grid), dim3(C2_THREADS), (size_t)smem, st, tm, tm_out, p);
   return launch_status();
 }
 
@@ -326,8 +358,18 @@ int dw_tc_conv2(const void *in, const float *w, const float *bias, void *out, in
   C2Params p{};
   p.N = N; p.C = C; p.H = H; p.W = W; p.k = k; p.dil = dil; p.pad = pad; p.flip = flip;
   p.rows_p = 128 + dil * (k - 1);
-  p.ks = ((W + dil - 1) / dil + 15) / 16;
   p.qoff = pad / dil;
+  const int Q = (W + dil - 1) / dil;  // columns of one phase
+  p.nt = (Q + 31) / 32;
+  if (p.nt == 1) {  // the whole phase is one N-tile: its K window is the phase itself (pad columns do not exist)
+    p.zpad = 0;
+    p.ks = (Q + 15) / 16;
+    p.chunks_p = 4;
+  } else {          // N-tile t reduces over q' in [32t - qoff, 32t + 31 + k - 1 - qoff], walked from the aligned chunk below
+    p.zpad = (p.qoff + 7) / 8;
+    p.ks = ((31 + k - 1 - p.qoff + 8 * p.zpad) / 8 + 1 + 1) / 2;
+    p.chunks_p = 4 * (p.nt - 1) + 2 * p.ks;
+  }
   p.planes = N;
   p.splits = tc_unit_splits(C, N);
   p.pairs = (long)C * p.splits;
@@ -336,10 +378,13 @@ int dw_tc_conv2(const void *in, const float *w, const float *bias, void *out, in
   if (N == 0 || C == 0) return KDCC_OK;
   const char *dbg = getenv("KDCC_TC_DEBUG");
   p.dbg = dbg ? atoi(dbg) : 0;
+  // compile-time MMA schedules for the shapes that matter; every other supported shape takes the run-time loops
+  if (dil == 5 && p.nt == 1 && p.ks == 2) return conv2_launch<5, 1, 2>(in, p, st);  // Cityscapes: 9x9, dilation 5, 128 columns
+  if (dil == 1 && p.nt == 4 && p.ks == 3) return conv2_launch<1, 4, 3>(in, p, st);  // 3x3 on a 128-column plane
   switch (dil) {
-    case 1: return conv2_launch<1>(in, p, st);
-    case 2: return conv2_launch<2>(in, p, st);
-    case 5: return conv2_launch<5>(in, p, st);
+    case 1: return conv2_launch<1, 0, 0>(in, p, st);
+    case 2: return conv2_launch<2, 0, 0>(in, p, st);
+    case 5: return conv2_launch<5, 0, 0>(in, p, st);
     default: return KDCC_ESHAPE;
   }
 }
