@@ -12,7 +12,7 @@ python bench.py $A > gpurun_out/plain_a.json 2> gpurun_out/plain_a.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py $A > gpurun_out/ncu_launches.out 2>&1
 echo "launch list rc=$?"
 python bench.py $B > gpurun_out/plain_b.json 2> gpurun_out/plain_b.err || exit 1
-ncu --metrics $M --clock-control none -k regex:"$K" -s 279 -c 93 --csv --log-file gpurun_out/step_metrics.csv python bench.py $B > gpurun_out/ncu_step.out 2>&1
+ncu --metrics $M --clock-control none -k regex:"$K" -s 267 -c 89 --csv --log-file gpurun_out/step_metrics.csv python bench.py $B > gpurun_out/ncu_step.out 2>&1
 echo "step metrics rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:dw_tc_conv2 -s 70 -c 2 -o gpurun_out/prof_conv2 -f python bench.py $B > gpurun_out/ncu_full1.out 2>&1
 echo "full conv2 rc=$?"
