@@ -383,12 +383,8 @@ int dw_nhwc3_conv(const void *in, const float *w, const float *bias, void *out, 
   int rc = n3_map(&tm, in, p, N3_WARPS * p.Jb + 2);
   if (rc) return rc;
   const int smem = N3_STAGES * (((N3_WARPS * p.Jb + 2) * p.Vb * N3_VB + 127) & ~127) + 2 * N3_BAR;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(dw_nhwc3_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(dw_nhwc3_conv_kernel, smem, attr_cache)) return e;
   launch_pdl(dw_nhwc3_conv_kernel, dim3(p.ctas_per_group * p.vgroups), dim3(N3_THREADS), (size_t)smem, st, tm, p);
   return launch_status();
 }
@@ -411,12 +407,8 @@ int dw_nhwc3_wgrad(const void *x, const void *dy, float *dw, float *part, int N,
   if (rc) return rc;
   const int smem = N3_WSTAGES * ((((N3_WARPS * p.Jb + 2) * p.Vb * N3_VB + 127) & ~127) + ((N3_WARPS * p.Jb * p.Vb * N3_VB + 127) & ~127)) + 2 * N3_WBAR +
                    N3_THREADS * N3_CH * (int)sizeof(float);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(dw_nhwc3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(dw_nhwc3_wgrad_kernel, smem, attr_cache)) return e;
   launch_pdl(dw_nhwc3_wgrad_kernel, dim3(p.ctas_per_group * p.vgroups), dim3(N3_THREADS), (size_t)smem, st, tm_x, tm_dy, p);
   rc = launch_status();
   if (rc) return rc;

@@ -322,12 +322,8 @@ static int tc_conv_launch(const void *in, const DwTcParams &p0, cudaStream_t st)
   int rc = make_tmap_bf16(&tm, in, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const int smem = p.a_stages * p.nbox * p.box_bytes + b_bytes + 256 + 1024;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tc_conv_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(dw_tc_conv_kernel<NT, KS>, smem, attr_cache)) return e;
   const int grid = (int)min(p.pairs, (long)kNumSMs);
   dw_tc_conv_kernel<NT, KS><<<grid, TC_THREADS, smem, st>>>(tm, p);
   return launch_status();

@@ -342,12 +342,8 @@ static int conv2_launch(const void *in, C2Params p, cudaStream_t st) {
   if (rc) return rc;
   const int smem = 2 * C2_STG + 2 * D * p.chunks_p * p.rows_p * 16 + 2 * p.k * 2 * p.ks * C2_TZ_CHUNK + 128 + 8 * 32 * 16 * D * (D == 1 ? 4 : (D == 2 ? 2 : 1)) + 256 + 1024;
   if (smem > 227 * 1024 || D * p.nt * 32 > 256) return KDCC_ESHAPE;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tc_conv2_kernel<D, NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(dw_tc_conv2_kernel<D, NT, KS>, smem, attr_cache)) return e;
   const int grid = (int)min(p.pairs, (long)kNumSMs);
   launch_pdl(dw_tc_conv2_kernel<D, NT, KS>, dim3(grid), dim3(C2_THREADS), (size_t)smem, st, tm, tm_out, p);
   return launch_status();

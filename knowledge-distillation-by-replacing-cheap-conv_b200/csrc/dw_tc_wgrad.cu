@@ -350,12 +350,8 @@ static int wgrad_launch(const void *x, const void *dy, float *dw, float *part, c
   p.x_stages = min(p.single ? 2 : 4, (220 * 1024 - fixed) / (p.nbox * p.box_bytes));
   if (p.x_stages < 2) return KDCC_ESHAPE;
   const int smem = p.x_stages * p.nbox * p.box_bytes + fixed;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tc_wgrad_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(dw_tc_wgrad_kernel<K>, smem, attr_cache)) return e;
   const int grid = (int)min(p.pairs, (long)kNumSMs);
   dw_tc_wgrad_kernel<K><<<grid, WG_THREADS, smem, st>>>(tm_x, tm_dy, p);
   int rc = launch_status();

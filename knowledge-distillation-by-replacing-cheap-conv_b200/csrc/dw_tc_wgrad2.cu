@@ -291,12 +291,8 @@ static int wgrad2_launch(const void *x, const void *dy, float *dw, float *part, 
   if (rc) return rc;
   p.out = p.splits == 1 ? dw : part;
   const int smem = 2 * W2_STAGE + 2 * W2_DYBOX + 4 * 32 * W2_SCR_PITCH * 4 + 192 + 4 * K * K * 4 + 64 + 1024;
-  static int attr_done = 0;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tc_wgrad2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = 1;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(dw_tc_wgrad2_kernel<K>, smem, attr_cache)) return e;
   const int grid = (int)min(p.units, (long)kNumSMs);
   launch_pdl(dw_tc_wgrad2_kernel<K>, dim3(grid), dim3(W2_THREADS), (size_t)smem, st, tm_x, tm_dy, p);
   rc = launch_status();

@@ -434,12 +434,8 @@ static int conv_launch(const void *in, const float *w, const float *bias, void *
   if (rc) return rc;
   rc = nhwc_map(&tm_out, out, N, Ho, Wo, C, Cfg::CB, Cfg::TH, Cfg::TW, dil);
   if (rc) return rc;
-  static bool attr_set = false;  // idempotent; a benign race only repeats the call
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tma_conv_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::CONV_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(dw_tma_conv_kernel<Cfg>, Cfg::CONV_SMEM, attr_cache)) return e;
   const int grid = (int)min(p.total, (long)kNumSMs * Cfg::OCC);
   dw_tma_conv_kernel<Cfg><<<grid, Cfg::CONV_NT, Cfg::CONV_SMEM, st>>>(tm_in, tm_out, p);
   return launch_status();
@@ -479,12 +475,8 @@ static int wgrad_launch(const void *x, const void *dy, float *dw, float *part, i
   if (rc) return rc;
   rc = nhwc_map(&tm_dy, dy, N, Ho, Wo, C, Cfg::CB, Cfg::TH, Cfg::TW, dil);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dw_tma_wgrad_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::WG_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(dw_tma_wgrad_kernel<Cfg>, Cfg::WG_SMEM, attr_cache)) return e;
   dw_tma_wgrad_kernel<Cfg><<<p.ncb * p.splits, Cfg::WG_NT, Cfg::WG_SMEM, st>>>(tm_x, tm_dy, p);
   rc = launch_status();
   if (rc) return rc;

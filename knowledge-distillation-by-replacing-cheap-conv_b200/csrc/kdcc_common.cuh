@@ -44,6 +44,21 @@ static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device.  Function attributes are per device,
+// so the cache is per (call site, device); a benign race only repeats the idempotent call.
+template <typename F>
+static inline int ensure_dynamic_smem(F *kernel, int bytes, int (&cache)[16]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (bytes > cache[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    cache[dev] = bytes;
+  }
+  return 0;
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>

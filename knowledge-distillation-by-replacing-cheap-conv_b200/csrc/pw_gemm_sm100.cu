@@ -356,13 +356,8 @@ static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaS
     if (rc) return rc;
     p.tma_out = 1;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pw_gemm_sm100_kernel<BJ, A_MN, B_MN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static int attr_cache[16] = {0};
+  if (int e = ensure_dynamic_smem(pw_gemm_sm100_kernel<BJ, A_MN, B_MN>, Cfg::SMEM, attr_cache)) return e;
   const long items = (long)p.tiles_i * p.tiles_j * p.splits * (p.r_spans_batch ? 1 : p.batch);
   const int grid = (int)min(items, (long)kNumSMs);
   launch_pdl(pw_gemm_sm100_kernel<BJ, A_MN, B_MN>, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM, st, tm_a, tm_b, tm_out, p);
