@@ -8,10 +8,10 @@ from . import _abi
 from ._abi import KdccError, LIB_PATH
 from .blocks import DepthwiseSeparableBlock
 from .losses import EnsembleKLDivergenceLoss, KLDivergenceLoss, MSELoss, MultiTeacherKLDivergenceLoss, WeightedHintMSELoss
-from . import functional
+from . import checkpoint, functional
 from .student import DepthwiseStudent
 from .metrics import CityscapesMetricTracker, ConfusionMatrix
 from .trainer import GradBucket, LayerwiseStep
 
 __all__ = ["DepthwiseSeparableBlock", "DepthwiseStudent", "LayerwiseStep", "GradBucket", "ConfusionMatrix", "CityscapesMetricTracker", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MultiTeacherKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
-           "functional", "KdccError", "LIB_PATH"]
+           "functional", "checkpoint", "KdccError", "LIB_PATH"]
