@@ -47,12 +47,16 @@ struct GemmParams {
   int tma_out;                       // out_raw only: the epilogue stages 32 x 64 tiles in smem and TMA stores them
 };
 
-template <int BJ>
+// PAIR: two CTAs of a cluster (one TPC) work on one 256 x BJ tile with cta_group::2 MMAs: each loads its own 128 rows of
+// A and HALF of B, the tensor core reads the other half from the partner's shared memory.  Per CTA and reduction block
+// that is 32 KB instead of 48 KB from L2 -- the 1-CTA kernel is L2-bandwidth bound (9.7 TB/s of L2 traffic per step).
+template <int BJ, bool PAIR>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BI * GEMM_BR * 2;  // 16 KB
-  static constexpr int B_BYTES = BJ * GEMM_BR * 2;
+  static constexpr int BJ_CTA = PAIR ? BJ / 2 : BJ;       // B rows held by one CTA
+  static constexpr int B_BYTES = BJ_CTA * GEMM_BR * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BJ == 256 ? 4 : (BJ == 128 ? 6 : 8);
+  static constexpr int STAGES = PAIR ? 6 : (BJ == 256 ? 4 : (BJ == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BJ;  // double-buffered accumulator (power of two >= 32)
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;   // epilogue staging: 4 warps x 2 tiles of 32 rows x 128 bytes
   static constexpr int BAR_OFF = OUT_OFF + 4 * 2 * 4096;
@@ -73,19 +77,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
-template <int BJ, bool A_MN, bool B_MN>
+template <int BJ, bool A_MN, bool B_MN, int BI = GEMM_BI>
 __device__ __forceinline__ constexpr uint32_t umma_idesc() {
   // c_format F32 (bits 4-5 = 1), a/b format BF16 (bits 7-9 / 10-12 = 1), majors (bits 15, 16),
   // N >> 3 (bits 17-22), M >> 4 (bits 24-28)
   return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-         ((uint32_t)(BJ >> 3) << 17) | ((uint32_t)(GEMM_BI >> 4) << 24);
+         ((uint32_t)(BJ >> 3) << 17) | ((uint32_t)(BI >> 4) << 24);
 }
 
-template <int BJ, bool A_MN, bool B_MN>
+template <int BJ, bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
-  using Cfg = GemmCfg<BJ>;
+  using Cfg = GemmCfg<BJ, PAIR>;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;  // 0 = leader: issues the MMAs, owns the full / tempty barriers
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -99,33 +104,42 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (PAIR) ptx::cluster_sync();  // both CTAs are resident before the pair-wide TMEM allocation
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    // pair: the leader's full barrier collects one arrival per CTA and the bytes of both; its tempty barrier the
+    // epilogue warps of both CTAs; empty / tfull are signalled in both CTAs by multicast commits
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), PAIR ? 2 : 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), PAIR ? 8 : 4); }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tm_a);
     ptx::prefetch_tensormap(&tm_b);
     if (p.tma_out) ptx::prefetch_tensormap(&tm_out);
   }
-  if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)));
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_alloc_pair<Cfg::TMEM_COLS>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)));
+    else ptx::tmem_alloc<Cfg::TMEM_COLS>(ptx::smem_u32(const_cast<uint32_t *>(tmem_slot)));
+  }
   ptx::tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_prologue_done();  // the prologue overlapped the previous kernel's tail; global memory from here on
 
   const int out_batches = p.r_spans_batch ? 1 : p.batch;
-  const long items = (long)p.tiles_i * p.tiles_j * p.splits * out_batches;
+  const int tiles_iw = PAIR ? p.tiles_i / 2 : p.tiles_i;   // work items along i: tiles, or pairs of tiles
+  const long items = (long)tiles_iw * p.tiles_j * p.splits * out_batches;
   const int rb_per_split = (p.rblocks + p.splits - 1) / p.splits;
+  const long item0 = PAIR ? (long)(blockIdx.x >> 1) : (long)blockIdx.x;
+  const long item_step = PAIR ? (long)(gridDim.x >> 1) : (long)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
     int s = 0; uint32_t ph = 0;
-    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+    for (long item = item0; item < items; item += item_step) {
       const int split = (int)(item % p.splits);
       long tile = item / p.splits;
       // i fastest: CTAs running side by side share the (large) B tile and differ in the (small, L2-resident) A tile
-      const int ti = (int)(tile % p.tiles_i); tile /= p.tiles_i;
+      const int ti = (int)(tile % tiles_iw) * (PAIR ? 2 : 1) + (int)rank; tile /= tiles_iw;
       const int tj = (int)(tile % p.tiles_j);
       const int bo = (int)(tile / p.tiles_j);  // output batch entry
       const int rb0 = split * rb_per_split, rb1 = min(p.rblocks, rb0 + rb_per_split);
@@ -137,30 +151,35 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         ptx::mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t a_dst = smem_base + s * Cfg::STAGE_BYTES;
         const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-        ptx::mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+        auto load = [&](uint32_t dst, const CUtensorMap *m, int c0, int c1, int c2) {
+          if (PAIR) ptx::tma_load_3d_pair(dst, m, full_bar(s), c0, c1, c2);  // bytes are credited to the leader's barrier
+          else ptx::tma_load_3d(dst, m, full_bar(s), c0, c1, c2);
+        };
+        if (!PAIR) ptx::mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+        else if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+        else ptx::mbar_arrive_cluster(full_bar(s), 0);
+        const int jb = tj * BJ + (int)rank * Cfg::BJ_CTA;  // this CTA's part of the B tile
         if (!A_MN) {
-          ptx::tma_load_3d(a_dst, &tm_a, full_bar(s), rl * GEMM_BR, ti * GEMM_BI, za);
+          load(a_dst, &tm_a, rl * GEMM_BR, ti * GEMM_BI, za);
         } else {
 #pragma unroll
-          for (int b = 0; b < GEMM_BI / 64; ++b)
-            ptx::tma_load_3d(a_dst + b * 8192, &tm_a, full_bar(s), ti * GEMM_BI + b * 64, rl * GEMM_BR, za);
+          for (int b = 0; b < GEMM_BI / 64; ++b) load(a_dst + b * 8192, &tm_a, ti * GEMM_BI + b * 64, rl * GEMM_BR, za);
         }
         if (!B_MN) {
-          ptx::tma_load_3d(b_dst, &tm_b, full_bar(s), rl * GEMM_BR, tj * BJ, zb);
+          load(b_dst, &tm_b, rl * GEMM_BR, jb, zb);
         } else {
 #pragma unroll
-          for (int b = 0; b < BJ / 64; ++b)
-            ptx::tma_load_3d(b_dst + b * 8192, &tm_b, full_bar(s), tj * BJ + b * 64, rl * GEMM_BR, zb);
+          for (int b = 0; b < Cfg::BJ_CTA / 64; ++b) load(b_dst + b * 8192, &tm_b, jb + b * 64, rl * GEMM_BR, zb);
         }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = umma_idesc<BJ, A_MN, B_MN>();
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===== MMA issuer (pair: the leader CTA issues for both) =====
+    constexpr uint32_t idesc = umma_idesc<BJ, A_MN, B_MN, PAIR ? 2 * GEMM_BI : GEMM_BI>();
     int s = 0; uint32_t ph = 0;
     int as = 0; uint32_t aph = 0;
-    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+    for (long item = item0; item < items; item += item_step) {
       const int split = (int)(item % p.splits);
       const int rb0 = split * rb_per_split, rb1 = min(p.rblocks, rb0 + rb_per_split);
       ptx::mbar_wait(tempty_bar(as), aph ^ 1);
@@ -176,12 +195,14 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           // K-major: step 16 elements (32 bytes) inside the swizzle atom; MN-major: step 16 r-rows (2 KB)
           const uint64_t da = A_MN ? umma_desc(a_addr + k * 2048, 8192, 1024) : umma_desc(a_addr + k * 32, 16, 1024);
           const uint64_t db = B_MN ? umma_desc(b_addr + k * 2048, 8192, 1024) : umma_desc(b_addr + k * 32, 16, 1024);
-          ptx::umma_f16(d_tmem, da, db, idesc, (rb > rb0 || k > 0) ? 1u : 0u);
+          if (PAIR) ptx::umma_f16_pair(d_tmem, da, db, idesc, (rb > rb0 || k > 0) ? 1u : 0u);
+          else ptx::umma_f16(d_tmem, da, db, idesc, (rb > rb0 || k > 0) ? 1u : 0u);
         }
-        ptx::umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+        if (PAIR) ptx::umma_commit_pair(empty_bar(s)); else ptx::umma_commit(empty_bar(s));
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      ptx::umma_commit(tfull_bar(as));   // accumulator complete -> epilogue
+      if (PAIR) ptx::umma_commit_pair(tfull_bar(as)); else ptx::umma_commit(tfull_bar(as));   // accumulator complete -> epilogue
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else if (warp >= 2) {
@@ -190,10 +211,10 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     int as = 0; uint32_t aph = 0;
     const uint32_t stage_tiles = Cfg::OUT_OFF + (uint32_t)(warp - 2) * 2 * 4096;
     int tn = 0;  // staging tiles written by this warp
-    for (long item = blockIdx.x; item < items; item += gridDim.x) {
+    for (long item = item0; item < items; item += item_step) {
       const int split = (int)(item % p.splits);
       long tile = item / p.splits;
-      const int ti = (int)(tile % p.tiles_i); tile /= p.tiles_i;
+      const int ti = (int)(tile % tiles_iw) * (PAIR ? 2 : 1) + (int)rank; tile /= tiles_iw;
       const int tj = (int)(tile % p.tiles_j);
       const long tile_batch = tile / p.tiles_j;
       const long obase = tile_batch * p.out_batch_stride;
@@ -236,7 +257,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
         ptx::tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        if (lane == 0) { if (PAIR) ptx::mbar_arrive_cluster(tempty_bar(as), 0); else ptx::mbar_arrive(tempty_bar(as)); }
         if (++as == 2) { as = 0; aph ^= 1; }
         continue;
       }
@@ -293,15 +314,17 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       }
       ptx::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+      if (lane == 0) { if (PAIR) ptx::mbar_arrive_cluster(tempty_bar(as), 0); else ptx::mbar_arrive(tempty_bar(as)); }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
     if (p.tma_out && lane == 0) ptx::tma_store_wait_all();
   }
 
   ptx::tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();  // pair: the partner may still read this CTA's shared memory / signal its barriers
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base); else ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
 }
 
 // out[i] = sum_s part[s][i]   (fixed order)
@@ -329,9 +352,9 @@ static int gemm_map(CUtensorMap *m, const void *base, long inner, long outer, in
   return make_tmap_bf16(m, base, 3, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BJ, bool A_MN, bool B_MN>
+template <int BJ, bool A_MN, bool B_MN, bool PAIR>
 static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaStream_t st) {
-  using Cfg = GemmCfg<BJ>;
+  using Cfg = GemmCfg<BJ, PAIR>;
   GemmParams p = p0;
   p.tiles_i = ceil_div(p.I, GEMM_BI);
   p.tiles_j = ceil_div(p.J, BJ);
@@ -342,7 +365,7 @@ static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaS
   const int ba = p.a_batched ? p.batch : 1, bb = p.b_batched ? p.batch : 1;
   int rc = A_MN ? gemm_map(&tm_a, a, p.I, p.R, ba, 64) : gemm_map(&tm_a, a, p.R, p.I, ba, GEMM_BI);
   if (rc) return rc;
-  rc = B_MN ? gemm_map(&tm_b, b, p.J, p.R, bb, 64) : gemm_map(&tm_b, b, p.R, p.J, bb, BJ);
+  rc = B_MN ? gemm_map(&tm_b, b, p.J, p.R, bb, 64) : gemm_map(&tm_b, b, p.R, p.J, bb, Cfg::BJ_CTA);
   if (rc) return rc;
   // bf16 raw output only: TMA-store epilogue over out[batch][I][J]
   CUtensorMap tm_out = tm_a;
@@ -357,18 +380,39 @@ static int gemm_launch(const void *a, const void *b, const GemmParams &p0, cudaS
     p.tma_out = 1;
   }
   static int attr_cache[16] = {0};
-  if (int e = ensure_dynamic_smem(pw_gemm_sm100_kernel<BJ, A_MN, B_MN>, Cfg::SMEM, attr_cache)) return e;
-  const long items = (long)p.tiles_i * p.tiles_j * p.splits * (p.r_spans_batch ? 1 : p.batch);
-  const int grid = (int)min(items, (long)kNumSMs);
-  launch_pdl(pw_gemm_sm100_kernel<BJ, A_MN, B_MN>, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM, st, tm_a, tm_b, tm_out, p);
+  if (int e = ensure_dynamic_smem(pw_gemm_sm100_kernel<BJ, A_MN, B_MN, PAIR>, Cfg::SMEM, attr_cache)) return e;
+  const long items = (long)(PAIR ? p.tiles_i / 2 : p.tiles_i) * p.tiles_j * p.splits * (p.r_spans_batch ? 1 : p.batch);
+  if (!PAIR) {
+    const int grid = (int)min(items, (long)kNumSMs);
+    launch_pdl(pw_gemm_sm100_kernel<BJ, A_MN, B_MN, PAIR>, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM, st, tm_a, tm_b, tm_out, p);
+    return launch_status();
+  }
+  // one cluster of two CTAs (one TPC) per work item
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)min(items, (long)(kNumSMs / 2)));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, pw_gemm_sm100_kernel<BJ, A_MN, B_MN, PAIR>, tm_a, tm_b, tm_out, p);
   return launch_status();
 }
 
 template <bool A_MN, bool B_MN>
 static int gemm_dispatch_bj(const void *a, const void *b, const GemmParams &p, cudaStream_t st) {
-  if (p.J >= 256 && p.J % 256 == 0) return gemm_launch<256, A_MN, B_MN>(a, b, p, st);
-  if (p.J > 64) return gemm_launch<128, A_MN, B_MN>(a, b, p, st);
-  return gemm_launch<64, A_MN, B_MN>(a, b, p, st);
+  if (p.J >= 256 && p.J % 256 == 0) {
+    // CTA pairs need an even number of 128-row tiles; KDCC_PW_1CTA=1 keeps the single-CTA kernel (A/B measurements)
+    if (ceil_div(p.I, GEMM_BI) % 2 == 0 && !getenv("KDCC_PW_1CTA")) return gemm_launch<256, A_MN, B_MN, true>(a, b, p, st);
+    return gemm_launch<256, A_MN, B_MN, false>(a, b, p, st);
+  }
+  if (p.J > 64) return gemm_launch<128, A_MN, B_MN, false>(a, b, p, st);
+  return gemm_launch<64, A_MN, B_MN, false>(a, b, p, st);
 }
 
 bool pw_sm100_supported(long M, int K, int Nc, int batch, int layout) {
