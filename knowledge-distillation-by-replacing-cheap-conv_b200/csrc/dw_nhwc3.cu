@@ -24,10 +24,16 @@
 
 namespace kdcc {
 
-constexpr int N3_WARPS = 6;                 // pixel-column groups per CTA tile
+#ifndef KDCC_N3_WARPS
+#define KDCC_N3_WARPS 6
+#endif
+#ifndef KDCC_N3_OCC
+#define KDCC_N3_OCC 2
+#endif
+constexpr int N3_WARPS = KDCC_N3_WARPS;     // pixel-column groups per CTA tile
 constexpr int N3_THREADS = 32 * N3_WARPS;
 constexpr int N3_CH = 8;                    // channels per thread (one 16-byte vector; 4 = 8-byte vectors, more warps, measured slower)
-constexpr int N3_OCC = 2;                   // CTAs per SM (launch bounds): 192 threads x 168 registers
+constexpr int N3_OCC = KDCC_N3_OCC;                 // CTAs per SM (launch bounds): 192 threads x 168 registers
 constexpr int N3_PAIRS = N3_CH / 2;
 constexpr int N3_VB = 2 * N3_CH;            // bytes of one thread's vector
 constexpr int N3_TH = 32;                   // rows per CTA tile
@@ -46,6 +52,7 @@ struct N3Params {
   int tiles_h, tiles_w;      // tile = N3_TH rows x N3_WARPS * Jb columns
   int flip;
   int ctas_per_group;        // persistent CTAs per channel group
+  int prefill;               // ring stages filled ahead: stages - lag (the producer refills a stage `lag` arrivals after it was read)
   int dbg;                   // KDCC_TC_DEBUG (timing experiments): 1 skip the FMAs, 2 skip the TMA ring (compute on stale smem), 4 skip stores
 };
 
@@ -153,7 +160,7 @@ dw_nhwc3_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const N3Params p
     }
   };
   if (threadIdx.x == 0 && !(p.dbg & 2))
-    for (int k = 0; k < N3_STAGES - 1; ++k) issue_next();
+    for (int k = 0; k < p.prefill; ++k) issue_next();
   uint32_t count = 0;  // arrivals consumed
   const uint8_t *mine = smem + jt * px_bytes + vb * N3_VB;   // left neighbour of this thread's column inside a ring row
   for (long tile = slot; tile < tiles; tile += p.ctas_per_group) {
@@ -270,7 +277,7 @@ dw_nhwc3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
   };
   if (threadIdx.x == 0)
-    for (int k = 0; k < N3_WSTAGES - 1; ++k) issue_next();
+    for (int k = 0; k < p.prefill; ++k) issue_next();
   uint32_t count = 0;
   const uint8_t *mine = smem + jt * px_bytes + vb * N3_VB;
   for (long tile = slot; tile < tiles; tile += p.ctas_per_group) {
@@ -351,6 +358,11 @@ bool dw_nhwc3_supported(int C, int k, int dil, int pad) {
   return V % 32 == 0 || V == 2 || V == 4 || V == 8 || V == 16;  // (V == 1 would need a TMA box wider than 256 columns)
 }
 
+static int n3_lag() {  // measurement knob; the default is what bench.py and the tests run
+  const char *e = getenv("KDCC_N3_LAG");
+  return e ? max(1, atoi(e)) : 1;
+}
+
 static void n3_geometry(N3Params &p) {
   const int V = p.C / N3_CH;
   p.Vb = V >= 32 ? 32 : V;
@@ -380,6 +392,7 @@ int dw_nhwc3_conv(const void *in, const float *w, const float *bias, void *out, 
   const char *dbg = getenv("KDCC_TC_DEBUG");
   p.dbg = dbg ? atoi(dbg) : 0;
   CUtensorMap tm;
+  p.prefill = max(1, N3_STAGES - n3_lag());
   int rc = n3_map(&tm, in, p, N3_WARPS * p.Jb + 2);
   if (rc) return rc;
   const int smem = N3_STAGES * (((N3_WARPS * p.Jb + 2) * p.Vb * N3_VB + 127) & ~127) + 2 * N3_BAR;
@@ -400,6 +413,7 @@ int dw_nhwc3_wgrad(const void *x, const void *dy, float *dw, float *part, int N,
   N3Params p{};
   p.part = part; p.N = N; p.H = H; p.W = W; p.C = C;
   n3_geometry(p);
+  p.prefill = max(1, N3_WSTAGES - n3_lag());
   CUtensorMap tm_x, tm_dy;
   int rc = n3_map(&tm_x, x, p, N3_WARPS * p.Jb + 2);
   if (rc) return rc;

@@ -26,7 +26,17 @@ namespace kdcc {
 
 constexpr int GEMM_BI = 128;   // UMMA M
 constexpr int GEMM_BR = 64;    // reduction elements per stage = one 128-byte swizzle atom of bf16
-constexpr int GEMM_THREADS = 192;
+#ifndef KDCC_GEMM_EPI_WARPS
+#define KDCC_GEMM_EPI_WARPS 4
+#endif
+// Epilogue warps: 4 = one per TMEM lane quadrant; 8 = two per quadrant, each draining every other 64-column chunk.
+// Measured equal (same box, whole step: pw fwd 0.761 vs 0.758 ms, dX 0.855 vs 0.843): the short-K GEMMs whose tensor
+// pipe is only 50 % active (4096<-256 dX: 128 FLOP per L2 byte with 256-deep tiles) wait on operand traffic, not on the
+// drain, so the default stays 4 (tools/build_variant.sh builds the other one).
+constexpr int GEMM_EPI_WARPS = KDCC_GEMM_EPI_WARPS;
+constexpr int GEMM_EPI_HALVES = GEMM_EPI_WARPS / 4;
+constexpr int GEMM_EPI_TILES = GEMM_EPI_WARPS == 4 ? 2 : 1;   // staging tiles per epilogue warp (32 KB in all)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 struct GemmParams {
   int I, J, R;          // logical extents (R per batch entry)
@@ -58,8 +68,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = PAIR ? 6 : (BJ == 256 ? 4 : (BJ == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BJ;  // double-buffered accumulator (power of two >= 32)
-  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;   // epilogue staging: 4 warps x 2 tiles of 32 rows x 128 bytes
-  static constexpr int BAR_OFF = OUT_OFF + 4 * 2 * 4096;
+  static constexpr int OUT_OFF = STAGES * STAGE_BYTES;   // epilogue staging: tiles of 32 rows x 128 bytes per warp
+  static constexpr int BAR_OFF = OUT_OFF + GEMM_EPI_WARPS * GEMM_EPI_TILES * 4096;
   static constexpr int SMEM = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-byte alignment
 };
 
@@ -109,7 +119,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     // pair: the leader's full barrier collects one arrival per CTA and the bytes of both; its tempty barrier the
     // epilogue warps of both CTAs; empty / tfull are signalled in both CTAs by multicast commits
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), PAIR ? 2 : 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), PAIR ? 8 : 4); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), (PAIR ? 2 : 1) * GEMM_EPI_WARPS); }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tm_a);
     ptx::prefetch_tensormap(&tm_b);
@@ -208,8 +218,9 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   } else if (warp >= 2) {
     // ===== epilogue: TMEM -> registers -> global =====
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are accessible to this warp
+    const int half = (warp - 2) >> 2;  // which of the quadrant's warps: column chunks half, half + HALVES, ...
     int as = 0; uint32_t aph = 0;
-    const uint32_t stage_tiles = Cfg::OUT_OFF + (uint32_t)(warp - 2) * 2 * 4096;
+    const uint32_t stage_tiles = Cfg::OUT_OFF + (uint32_t)(warp - 2) * GEMM_EPI_TILES * 4096;
     int tn = 0;  // staging tiles written by this warp
     for (long item = item0; item < items; item += item_step) {
       const int split = (int)(item % p.splits);
@@ -226,18 +237,18 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         // bf16 output through shared memory: 32 rows x 64 columns per warp and chunk, 128B-swizzled, stored by TMA
         // (coalesced 128-byte rows; ragged edges are clipped by the tensor map)
 #pragma unroll 1
-        for (int ch = 0; ch < BJ / 64; ++ch) {
+        for (int ch = half; ch < BJ / 64; ch += GEMM_EPI_HALVES) {
           const int col0 = tj * BJ + ch * 64;
           if (col0 >= p.J) break;
           uint32_t v[64];
           ptx::tmem_ld_32x32b_x32(t_row + ch * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           ptx::tmem_ld_32x32b_x32(t_row + ch * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           ptx::tmem_ld_wait();
-          if (tn >= 2) {  // the store that read this tile two chunks ago has finished reading it
-            if (lane == 0) ptx::tma_store_wait_read1();
+          if (tn >= GEMM_EPI_TILES) {  // the store that last read this staging tile has finished reading it
+            if (lane == 0) { if (GEMM_EPI_TILES == 2) ptx::tma_store_wait_read1(); else ptx::tma_store_wait_read(); }
             __syncwarp();
           }
-          const uint32_t tile = stage_tiles + (uint32_t)(tn & 1) * 4096;
+          const uint32_t tile = stage_tiles + (uint32_t)(tn % GEMM_EPI_TILES) * 4096;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 o;
@@ -262,7 +273,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         continue;
       }
 #pragma unroll 1
-      for (int ch = 0; ch < BJ / 32; ++ch) {
+      for (int ch = half; ch < BJ / 32; ch += GEMM_EPI_HALVES) {
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + ch * 32, v);
         ptx::tmem_ld_wait();
