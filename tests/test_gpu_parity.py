@@ -169,6 +169,7 @@ SEEDED_NCHW = [
     (5, 8, 8, 16, 32, 5, 1, 2),         # undilated 5x5: a single phase exactly 32 columns wide
     (1, 8, 8, 128, 128, 3, 1, 1),       # 3x3 on a full plane: tiled Toeplitz conv + whole-plane weight gradient
     (2, 16, 8, 64, 64, 3, 2, 2),        # dilation 2, two phases of 32 columns
+    (1, 16, 8, 128, 256, 9, 5, 20),     # Gated-SCNN site shape (1024 x 2048 input): two 128-column tiles per plane
 ]
 
 
