@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KDCC_VERSION 102 /* round 1: layout-aware depthwise/pointwise, confusion matrix */
+#define KDCC_VERSION 103 /* round 1: layout-aware depthwise/pointwise, confusion matrix, multi-teacher KD, TTA stitch */
 
 enum { KDCC_F32 = 0, KDCC_BF16 = 1 };
 enum { KDCC_LAYOUT_NHWC = 0, KDCC_LAYOUT_NCHW = 1 };
@@ -147,6 +147,19 @@ size_t kdcc_colsum_workspace_bytes(long M, int Nc);
 int kdcc_confusion_update(const void *logits, const long long *labels, long long *conf, int N, int C, long HW,
                           long batch_stride, long class_stride, int ignore_index, int dtype,
                           kdcc_stream_t stream);
+
+/* ---- sliding-window test-time inference -------------------------------------------
+ * kdcc_tta_stitch replaces utils/tta_process.py:39-52 (collect_windows_result) and the np.fliplr of :19-20:
+ * out[c][y][x] (+)= alpha * S[c][y][flip ? w-1-x : x],  S = (sum of the windows covering the pixel) / count.
+ * windows fp32 [n][C][th][tw] on the device; coords int32 [n][4] = (x1, y1, x2, y2) on the device, 16-byte aligned,
+ * x2-x1 <= tw, y2-y1 <= th (a window is cropped to the part inside the image).  count_mode 0 = the reference's
+ * counter exactly as written (:46, a (classes, h, w) array sliced [y1:y2, x1:x2]: identical results, including
+ * inf/nan where it is 0); 1 = per-pixel coverage.  n <= 512.
+ * kdcc_resize_bilinear replaces resize_output (:29-36, cv2.INTER_LINEAR per class plane): dst (+)= alpha * resize. */
+int kdcc_tta_stitch(const float *windows, const int *coords, int n, int C, int th, int tw, int h, int w, int flip,
+                    int count_mode, float alpha, float *out, int accumulate, kdcc_stream_t stream);
+int kdcc_resize_bilinear(const float *src, int C, int h, int w, float *dst, int H, int W, float alpha, int accumulate,
+                         kdcc_stream_t stream);
 
 #ifdef __cplusplus
 }

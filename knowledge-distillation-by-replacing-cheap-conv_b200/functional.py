@@ -377,3 +377,43 @@ def confusion_update(conf, logits, target, ignore_index=255):
     _abi.check(_abi.lib().kdcc_confusion_update(_ptr(logits), _ptr(target), _ptr(conf), N, C, HW, C * HW, HW, int(ignore_index),
                                                 _dtype_code(logits), _stream()), "kdcc_confusion_update")
     return conf
+
+
+# ---------------------------------------------------------------------------------------------------
+# sliding-window test-time inference
+# ---------------------------------------------------------------------------------------------------
+_COUNT_MODES = {"reference": 0, "coverage": 1}
+
+
+@torch.no_grad()
+def tta_stitch(windows, coords, h, w, out, flip=False, count_mode="reference", alpha=1.0, accumulate=False):
+    """out (C, h, w) fp32 (+)= alpha * overlap-add of `windows` (n, C, th, tw) placed at `coords` (n, 4) int32 device
+    tensor of (x1, y1, x2, y2), divided by the window counter -- utils/tta_process.py:39-52; flip=True un-mirrors the
+    stitched map (the np.fliplr of :19-20).  count_mode "reference" keeps the reference's counter as written."""
+    _require_cuda(windows, coords, out)
+    if windows.dtype != torch.float32 or out.dtype != torch.float32 or coords.dtype != torch.int32:
+        raise _abi.KdccError("tta_stitch needs fp32 windows / output and int32 coordinates")
+    if not (windows.is_contiguous() and out.is_contiguous() and coords.is_contiguous()):
+        raise _abi.KdccError("tta_stitch needs contiguous tensors")
+    n, C, th, tw = windows.shape
+    if coords.numel() != 4 * n or out.numel() != C * h * w:
+        raise _abi.KdccError("tta_stitch: %d windows of %d classes do not match coords %s / output %s"
+                             % (n, C, tuple(coords.shape), tuple(out.shape)))
+    _abi.check(_abi.lib().kdcc_tta_stitch(_ptr(windows), _ptr(coords), n, C, th, tw, int(h), int(w), int(bool(flip)),
+                                          _COUNT_MODES[count_mode], float(alpha), _ptr(out), int(bool(accumulate)), _stream()),
+               "kdcc_tta_stitch")
+    return out
+
+
+@torch.no_grad()
+def resize_bilinear(src, out, alpha=1.0, accumulate=False):
+    """out (C, H, W) (+)= alpha * cv2.INTER_LINEAR resize of every plane of src (C, h, w) -- utils/tta_process.py:29-36."""
+    _require_cuda(src, out)
+    if src.dtype != torch.float32 or out.dtype != torch.float32 or not (src.is_contiguous() and out.is_contiguous()):
+        raise _abi.KdccError("resize_bilinear needs contiguous fp32 tensors")
+    C, h, w = src.shape
+    if out.shape[0] != C:
+        raise _abi.KdccError("resize_bilinear: %d source planes, %d destination planes" % (C, out.shape[0]))
+    _abi.check(_abi.lib().kdcc_resize_bilinear(_ptr(src), C, h, w, _ptr(out), out.shape[1], out.shape[2], float(alpha),
+                                               int(bool(accumulate)), _stream()), "kdcc_resize_bilinear")
+    return out

@@ -8,8 +8,8 @@ attributes (`teacher`, `student`, `student_hidden_outputs`, `teacher_hidden_outp
 only functional difference is the block class that `replace` instantiates: the kdcc
 `DepthwiseSeparableBlock` whose convolutions run in libkdcc.so.
 
-Out of scope here (reference features that are not on the distillation hot path): `inference_test`
-(sliding-window TTA, utils/tta_process.py) and the BeautifulTable rendering of the block report.
+`inference_test` (sliding-window TTA) stitches on the GPU, see kdcc/tta.py.  Out of scope here: the BeautifulTable
+rendering of the block report.
 """
 import copy
 import gc
@@ -123,6 +123,14 @@ class DepthwiseStudent(nn.Module):
         self.student_hidden_outputs = []
         self.teacher_hidden_outputs = []
         return self.student(x)
+
+    def inference_test(self, data, args):
+        """Sliding-window multi-scale + mirrored inference of the student (depthwise_student.py:187-206); the windows
+        are stitched on the device with the reference's normalisation (kdcc.tta.reverse_mapping)."""
+        from . import tta
+        self.student_hidden_outputs = []
+        self.teacher_hidden_outputs = []
+        return tta.inference_test(self.student, data, args)
 
     def train(self, mode=True):
         self.save_hidden = bool(mode)

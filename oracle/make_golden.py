@@ -108,6 +108,41 @@ def metrics_golden():
     np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
 
 
+def tta_golden():
+    """utils/tta_process.py run end to end on small seeded images: window list, crops and reverse_mapping of seeded
+    window outputs (scale 1.0 as in every shipped config, one equal-tile two-scale case).  The module predates
+    numpy 1.24 (`np.float`, :51), so that alias is restored before it is loaded; nothing else is shimmed."""
+    from PIL import Image
+    np.float = float
+    ref = _load("ref_tta", "utils/tta_process.py")
+    mean_std = ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    rs = np.random.RandomState(77)
+    out = {}
+    #          W   H  crop scales     classes
+    cases = [(60, 36, 24, [1.0], 5),       # 4 x 2 windows, fewer classes than tile rows: the reference counter covers every class
+             (48, 48, 24, [1.0], 19),      # square, 3 x 3 windows
+             (50, 30, 28, [1.0], 7),       # windows pulled back at both borders
+             (40, 20, 20, [1.0, 1.0], 4),  # two scales (equal tiles, the only multi-scale form the reference can batch)
+             (36, 18, 18, [1.0], 24)]      # more classes than the tile is high: rows of the counter stay 0 -> inf / nan
+    for i, (W, H, crop, scales, C) in enumerate(cases):
+        img = Image.fromarray(rs.randint(0, 255, (H, W, 3)).astype(np.uint8))
+        ori, mapping, windows = ref.get_crops_image(ref.scale_and_flip_image(img, mean_std, scales), scales, crop_size=crop)
+        # window outputs are NOT stored: tests regenerate them from this seed (legacy RandomState streams are stable)
+        seed = 1000 + i
+        res = np.random.RandomState(seed).standard_normal((windows.shape[0], C, windows.shape[2], windows.shape[3])).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            full = ref.reverse_mapping(mapping, res, ori)
+        out["c%d/image" % i] = np.asarray(img)
+        out["c%d/args" % i] = np.array([W, H, crop, C, len(scales), seed, windows.shape[0]], np.int64)
+        out["c%d/scales" % i] = np.array(scales, np.float64)
+        if i == 0:
+            out["c%d/windows" % i] = windows.numpy()   # pins the crop order / mirroring of get_crops_image
+        out["c%d/full" % i] = full.astype(np.float32)
+        for k, (w, h, boxes) in enumerate(mapping):
+            out["c%d/map%d" % (i, k)] = np.array([[w, h, 0, 0]] + [list(b) for b in boxes], np.int64)
+    np.savez_compressed(os.path.join(OUT, "tta.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # deterministic reduction order
@@ -177,7 +212,8 @@ def main():
 
     metrics_golden()
     ensemble_golden()
-    for fn in ("block.npz", "losses.npz", "metrics.npz", "ensemble.npz"):
+    tta_golden()
+    for fn in ("block.npz", "losses.npz", "metrics.npz", "ensemble.npz", "tta.npz"):
         print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")
 
 

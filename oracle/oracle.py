@@ -178,3 +178,82 @@ def kd_loss_multi(s, teachers, weights, T=1.0, need_grad=True):
         if need_grad:
             ds += np.float32(w) * g
     return loss, ds
+
+
+# ---- sliding-window test-time stitching -----------------------------------------------------
+def tta_window_coordinates(w, h, tile, overlap=1 / 3):
+    """Window list of utils/tta_process.py:81-105 (get_crops_image) for one scaled image of size (w, h): square
+    tiles of `tile`, stride ceil(tile * (1 - overlap)), the last window of every axis pulled back inside the image,
+    x outer / y inner.  Returns [(x1, y1, x2, y2)]."""
+    import math
+    stride = math.ceil(tile * (1 - overlap))
+    nx = int(math.ceil((w - tile) / stride) + 1)
+    ny = int(math.ceil((h - tile) / stride) + 1)
+    out = []
+    for ix in range(nx):
+        for iy in range(ny):
+            x2, y2 = min(ix * stride + tile, w), min(iy * stride + tile, h)
+            out.append((max(x2 - tile, 0), max(y2 - tile, 0), x2, y2))
+    return out
+
+
+def tta_collect(w, h, coords, windows, count_mode="reference"):
+    """Overlap-add of window outputs, restating utils/tta_process.py:39-52 (collect_windows_result).  The sum is the
+    plain overlap-add (:49-51, a window is cropped to the part inside the image).  count_mode "reference" keeps the
+    reference's counter as written (:46 indexes the (classes, h, w) counter with [y1:y2, x1:x2], i.e. classes by the
+    y range and ROWS by the x range, all columns); "coverage" is the per-pixel coverage count.  float64 (C, h, w)."""
+    windows = np.asarray(windows)
+    C = windows.shape[1]
+    full = np.zeros((C, h, w))
+    cnt = np.zeros((C, h, w))
+    for win, (x1, y1, x2, y2) in zip(windows, coords):
+        if count_mode == "reference":
+            cnt[y1:y2, x1:x2] += 1
+        else:
+            cnt[:, y1:y2, x1:x2] += 1
+        full[:, y1:y2, x1:x2] += win[:, :y2 - y1, :x2 - x1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return full / cnt
+
+
+def tta_resize_bilinear(planes, out_w, out_h):
+    """cv2.resize(plane, (out_w, out_h), interpolation=cv2.INTER_LINEAR) for every 2-D plane (utils/tta_process.py:
+    29-36), restated: source coordinate (d + 0.5) * in/out - 0.5, taps floor and floor + 1 clamped to the plane, the
+    fractional weight rounded to float32 (OpenCV keeps its interpolation table in float), arithmetic in float64.
+    Same size = copy (as cv2); a tap of weight 0 is not read, so inf entries do not turn their neighbours into nan."""
+    planes = np.asarray(planes, np.float64)
+    C, h, w = planes.shape
+    if (out_w, out_h) == (w, h):
+        return planes.copy()
+
+    def taps(n_in, n_out):
+        f = ((np.arange(n_out) + 0.5) * (n_in / n_out) - 0.5).astype(np.float32)
+        i0 = np.floor(f).astype(np.int64)
+        frac = (f - i0).astype(np.float32)
+        frac[i0 < 0] = 0.0
+        frac[i0 >= n_in - 1] = 0.0
+        i0 = np.clip(i0, 0, n_in - 1)
+        i1 = np.clip(i0 + 1, 0, n_in - 1)
+        return i0, i1, frac.astype(np.float64)
+
+    y0, y1, fy = taps(h, out_h)
+    x0, x1, fx = taps(w, out_w)
+    with np.errstate(invalid="ignore"):
+        rows = np.where(fx > 0, planes[:, :, x0] * (1 - fx) + planes[:, :, x1] * fx, planes[:, :, x0])   # horizontal pass
+        fy3 = fy[None, :, None]
+        return np.where(fy3 > 0, rows[:, y0, :] * (1 - fy3) + rows[:, y1, :] * fy3, rows[:, y0, :])
+
+
+def tta_reverse_mapping(mapping, results, ori_size, count_mode="reference"):
+    """utils/tta_process.py:9-26 (reverse_mapping): per scale, stitch the plain and the mirrored windows, un-mirror
+    the latter, resize both to ori_size = (w, h) and average.  results: all windows in order (plain then mirrored per
+    scale).  Returns float64 (n_scales, C, h_ori, w_ori)."""
+    results = np.asarray(results)
+    out, idx = [], 0
+    for w, h, coords in mapping:
+        n = len(coords)
+        plain = tta_collect(w, h, coords, results[idx:idx + n], count_mode)
+        mirrored = tta_collect(w, h, coords, results[idx + n:idx + 2 * n], count_mode)[:, :, ::-1]
+        out.append((tta_resize_bilinear(plain, *ori_size) + tta_resize_bilinear(mirrored, *ori_size)) / 2)
+        idx += 2 * n
+    return np.stack(out)
