@@ -86,6 +86,15 @@ int kdcc_pw_fwd(const void *x, const void *w, const float *scale, const float *s
                 void *y_raw, void *y_act, long M, int K, int Nc, int batch, int layout, int dtype,
                 kdcc_stream_t stream);
 
+/* The same with the block's shortcut folded into the epilogue:
+ *   y_act = relu?( out * scale[n] + shift[n] + residual )
+ * replaces `out = self.convs(bn1); out.add_(shortcut)` of the teacher's residual blocks when the replaced conv is
+ * the last of `convs` (wider_resnet.py:181; 4 of the 9 sites of cfg/cityscapes/51M_deeplab_all.json).  residual has
+ * the layout and dtype of y_act, which is required; y_raw (pre-add) stays optional. */
+int kdcc_pw_fwd_residual(const void *x, const void *w, const float *scale, const float *shift, const void *residual,
+                         int relu, void *y_raw, void *y_act, long M, int K, int Nc, int batch, int layout, int dtype,
+                         kdcc_stream_t stream);
+
 /* Autograd backward of the call above.  dx[m][k] = sum_n dy[m][n] w[n][k];
  * dw[n][k] = sum_m dy[m][n] x[m][k] (fp32 out, deterministic split-M reduction). */
 size_t kdcc_pw_bwd_workspace_bytes(int which /*0 = dx, 1 = dw*/, long M, int K, int Nc, int dtype);

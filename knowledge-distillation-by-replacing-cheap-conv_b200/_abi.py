@@ -24,6 +24,7 @@ SIGNATURES = {
     "kdcc_dw_bwd_workspace_bytes": (_sz, [_i] * 9),
     "kdcc_dw_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "kdcc_pw_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp]),
+    "kdcc_pw_fwd_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp]),
     "kdcc_pw_bwd_workspace_bytes": (_sz, [_i, _l, _i, _i, _i]),
     "kdcc_pw_bwd_dx": (_i, [_vp, _vp, _vp, _vp, _sz, _l, _i, _i, _i, _i, _i, _vp]),
     "kdcc_pw_bwd_dw": (_i, [_vp, _vp, _vp, _vp, _sz, _l, _i, _i, _i, _i, _i, _vp]),

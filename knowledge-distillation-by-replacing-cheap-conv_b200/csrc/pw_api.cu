@@ -27,23 +27,36 @@ static int check(long M, int K, int Nc, int batch, int layout, int dtype) {
   return KDCC_OK;
 }
 
-KDCC_API int kdcc_pw_fwd(const void *x, const void *w, const float *scale, const float *shift, int relu, void *y_raw,
-                         void *y_act, long M, int K, int Nc, int batch, int layout, int dtype, kdcc_stream_t stream) {
+static int pw_fwd_impl(const void *x, const void *w, const float *scale, const float *shift, const void *residual, int relu,
+                       void *y_raw, void *y_act, long M, int K, int Nc, int batch, int layout, int dtype, kdcc_stream_t stream) {
   int rc = check(M, K, Nc, batch, layout, dtype);
   if (rc) return rc;
   if (M == 0) return KDCC_OK;
-  if (!x || !w || (!y_raw && !y_act)) return KDCC_EINVAL;
+  if (!x || !w || (!y_raw && !y_act) || (residual && !y_act)) return KDCC_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_sm100(M, K, Nc, batch, layout, dtype)) {
-    if (!aligned16(x) || !aligned16(w) || (y_raw && !aligned16(y_raw)) || (y_act && !aligned16(y_act))) return KDCC_EALIGN;
-    return pw_sm100_fwd(x, w, scale, shift, relu, y_raw, y_act, M, K, Nc, batch, layout, st);
+    if (!aligned16(x) || !aligned16(w) || (y_raw && !aligned16(y_raw)) || (y_act && !aligned16(y_act)) ||
+        (residual && !aligned16(residual)))
+      return KDCC_EALIGN;
+    return pw_sm100_fwd(x, w, scale, shift, residual, relu, y_raw, y_act, M, K, Nc, batch, layout, st);
   }
   if (layout == KDCC_LAYOUT_NCHW) return KDCC_ESHAPE;
   SimtGemm g{};
   g.I = (int)M; g.J = Nc; g.R = K;
   g.sai = K; g.sar = 1; g.sbj = K; g.sbr = 1; g.splits = 1;
-  g.out_raw = y_raw; g.out_act = y_act; g.scale = scale; g.shift = shift; g.relu = relu;
+  g.out_raw = y_raw; g.out_act = y_act; g.scale = scale; g.shift = shift; g.relu = relu; g.residual = residual;
   return dtype == KDCC_F32 ? pw_simt_gemm<float>(x, w, g, st) : pw_simt_gemm<__nv_bfloat16>(x, w, g, st);
+}
+
+KDCC_API int kdcc_pw_fwd(const void *x, const void *w, const float *scale, const float *shift, int relu, void *y_raw,
+                         void *y_act, long M, int K, int Nc, int batch, int layout, int dtype, kdcc_stream_t stream) {
+  return pw_fwd_impl(x, w, scale, shift, nullptr, relu, y_raw, y_act, M, K, Nc, batch, layout, dtype, stream);
+}
+
+KDCC_API int kdcc_pw_fwd_residual(const void *x, const void *w, const float *scale, const float *shift, const void *residual,
+                                  int relu, void *y_raw, void *y_act, long M, int K, int Nc, int batch, int layout, int dtype,
+                                  kdcc_stream_t stream) {
+  return pw_fwd_impl(x, w, scale, shift, residual, relu, y_raw, y_act, M, K, Nc, batch, layout, dtype, stream);
 }
 
 KDCC_API size_t kdcc_pw_bwd_workspace_bytes(int which, long M, int K, int Nc, int dtype) {

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) pw_simt_kernel(const T *__restrict__ A, c
           float x = v;
           if (g.scale) x *= g.scale[gj];
           if (g.shift) x += g.shift[gj];
+          if (g.residual) x += to_f32(static_cast<const T *>(g.residual)[(long)gi * g.J + gj]);
           if (g.relu) x = fmaxf(x, 0.f);
           static_cast<T *>(g.out_act)[(long)gi * g.J + gj] = from_f32<T>(x);
         }

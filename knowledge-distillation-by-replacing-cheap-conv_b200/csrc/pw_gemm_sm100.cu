@@ -52,6 +52,7 @@ struct GemmParams {
   // epilogue
   __nv_bfloat16 *out_raw, *out_act;  // [I][J] bf16, either may be null
   const float *scale, *shift;        // per j, may be null
+  const __nv_bfloat16 *residual;     // [I][J] like out_act, added before the activation (the block's shortcut); may be null
   int relu;
   float *out_f32;                    // [splits][I][J] fp32 partials (dW) -- exclusive with the bf16 outputs
   int tma_out;                       // out_raw only: the epilogue stages 32 x 64 tiles in smem and TMA stores them
@@ -304,13 +305,19 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 if (col0 + q * 8 < p.J) {
-                  float f[8];
+                  float f[8], r[8];
+                  if (p.residual) {
+                    const uint4 rv = __ldg(reinterpret_cast<const uint4 *>(p.residual + obase + (long)row * p.J + col0 + q * 8));
+                    r[0] = bf16lo(rv.x); r[1] = bf16hi(rv.x); r[2] = bf16lo(rv.y); r[3] = bf16hi(rv.y);
+                    r[4] = bf16lo(rv.z); r[5] = bf16hi(rv.z); r[6] = bf16lo(rv.w); r[7] = bf16hi(rv.w);
+                  }
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
                     const int ch = p.affine_rows ? row : col0 + q * 8 + e;
                     float x = __uint_as_float(v[8 * q + e]);
                     if (p.scale) x *= __ldg(p.scale + ch);
                     if (p.shift) x += __ldg(p.shift + ch);
+                    if (p.residual) x += r[e];
                     if (p.relu) x = fmaxf(x, 0.f);
                     f[e] = x;
                   }
@@ -433,12 +440,13 @@ bool pw_sm100_supported(long M, int K, int Nc, int batch, int layout) {
   return Nc % 8 == 0;
 }
 
-int pw_sm100_fwd(const void *x, const void *w, const float *scale, const float *shift, int relu, void *y_raw,
-                 void *y_act, long M, int K, int Nc, int batch, int layout, cudaStream_t st) {
+int pw_sm100_fwd(const void *x, const void *w, const float *scale, const float *shift, const void *residual, int relu,
+                 void *y_raw, void *y_act, long M, int K, int Nc, int batch, int layout, cudaStream_t st) {
   GemmParams p{};
   p.out_raw = static_cast<__nv_bfloat16 *>(y_raw);
   p.out_act = static_cast<__nv_bfloat16 *>(y_act);
   p.scale = scale; p.shift = shift; p.relu = relu; p.splits = 1;
+  p.residual = static_cast<const __nv_bfloat16 *>(residual);
   if (layout == KDCC_LAYOUT_NHWC) {
     // y[m][n] = sum_k x[m][k] w[n][k]
     p.I = (int)M; p.J = Nc; p.R = K; p.batch = 1;

@@ -130,7 +130,7 @@ def depthwise_conv(x, weight, bias, kernel_size, dilation, padding):
 # ---------------------------------------------------------------------------------------------------
 class _PointwiseConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, scale, shift, relu):
+    def forward(ctx, x, weight, bias, scale, shift, relu, residual=None):
         _require_cuda(x, weight, bias)
         N, K, H, W = x.shape
         Co = weight.shape[0]
@@ -148,14 +148,22 @@ class _PointwiseConv(torch.autograd.Function):
             eff_shift = bias.detach().float().contiguous()
         elif bias is not None:
             raise _abi.KdccError("conv bias together with a fused BN epilogue is not supported; fold the bias into shift")
-        use_act = fused or bias is not None
-        _abi.check(_abi.lib().kdcc_pw_fwd(_ptr(x), _ptr(w), _ptr(scale), _ptr(eff_shift), int(bool(relu)),
-                                          None if use_act else _ptr(y), _ptr(y) if use_act else None,
-                                          M, K, Co, N, layout, code, _stream()), "kdcc_pw_fwd")
+        use_act = fused or bias is not None or residual is not None
+        if residual is not None:
+            if residual.shape != y.shape:
+                raise _abi.KdccError("residual %s does not match the output %s" % (tuple(residual.shape), tuple(y.shape)))
+            res = _format(residual.detach().to(x.dtype), layout)
+            _abi.check(_abi.lib().kdcc_pw_fwd_residual(_ptr(x), _ptr(w), _ptr(scale), _ptr(eff_shift), _ptr(res), int(bool(relu)),
+                                                       None, _ptr(y), M, K, Co, N, layout, code, _stream()), "kdcc_pw_fwd_residual")
+        else:
+            _abi.check(_abi.lib().kdcc_pw_fwd(_ptr(x), _ptr(w), _ptr(scale), _ptr(eff_shift), int(bool(relu)),
+                                              None if use_act else _ptr(y), _ptr(y) if use_act else None,
+                                              M, K, Co, N, layout, code, _stream()), "kdcc_pw_fwd")
         if fused:
             ctx.mark_non_differentiable(y)  # inference-only epilogue (eval-mode BN fold)
         ctx.save_for_backward(x, w)
         ctx.meta = (bias is not None, weight.shape, layout)
+        ctx.has_residual = residual is not None
         return y
 
     @staticmethod
@@ -184,12 +192,16 @@ class _PointwiseConv(torch.autograd.Function):
             dyr = _nhwc(dy)  # column sums are taken over the pixel-major view
             ws = _workspace(L.kdcc_colsum_workspace_bytes(M, Co), x.device)
             _abi.check(L.kdcc_colsum(_ptr(dyr), _ptr(db), _ptr(ws), ws.numel(), M, Co, code, st), "kdcc_colsum")
-        return dx, dw, db, None, None, None
+        # y = conv + residual: the shortcut receives the output gradient as it is
+        dres = dy if (ctx.has_residual and ctx.needs_input_grad[6]) else None
+        return dx, dw, db, None, None, None, dres
 
 
-def pointwise_conv(x, weight, bias=None, scale=None, shift=None, relu=False):
-    """F.conv2d(x, weight (Co,C,1,1), bias) on libkdcc; optional fused eval-mode BN (scale, shift) + ReLU."""
-    return _PointwiseConv.apply(x, weight, bias, scale, shift, bool(relu))
+def pointwise_conv(x, weight, bias=None, scale=None, shift=None, relu=False, residual=None):
+    """F.conv2d(x, weight (Co,C,1,1), bias) on libkdcc; optional fused eval-mode BN (scale, shift) + ReLU, optional
+    shortcut added in the epilogue (`out = convs(x); out.add_(shortcut)` of a residual block in one kernel;
+    differentiable when no BN / ReLU is fused)."""
+    return _PointwiseConv.apply(x, weight, bias, scale, shift, bool(relu), residual)
 
 
 # ---------------------------------------------------------------------------------------------------

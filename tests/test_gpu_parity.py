@@ -267,6 +267,41 @@ def test_pointwise_fused_bn_relu_epilogue(kdcc):
     assert relerr(host(y), ref) < TOL[torch.bfloat16]
 
 
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pointwise_residual_epilogue(kdcc, layout, dtype):
+    """`out = conv(x); out.add_(shortcut)` (wider_resnet.py:181) in one kernel: forward, and the gradients of x, w
+    and the shortcut, against the oracle GEMM plus a host add; with BN fold + ReLU on top (inference form)."""
+    if dtype == torch.float32 and layout == "nchw":
+        pytest.skip("the NCHW pointwise form exists on the bf16 tensor-core path only")
+    from oracle import oracle as orc
+    rs = np.random.RandomState(11)
+    N, K, Nc, H, W = 2, 64, 128, 16, 24
+    x = q(rs.standard_normal((N, K, H, W)).astype(np.float32), dtype)
+    w = q((rs.uniform(-1, 1, (Nc, K, 1, 1)) / np.sqrt(K)).astype(np.float32), dtype)
+    r = q(rs.standard_normal((N, Nc, H, W)).astype(np.float32), dtype)
+    dy = q(rs.standard_normal((N, Nc, H, W)).astype(np.float32), dtype)
+    fmt = torch.contiguous_format if layout == "nchw" else torch.channels_last
+    xt = to_dev(x, dtype).contiguous(memory_format=fmt).requires_grad_(True)
+    rt = to_dev(r, dtype).contiguous(memory_format=fmt).requires_grad_(True)
+    wt = torch.from_numpy(w).cuda().requires_grad_(True)
+    y = kdcc.functional.pointwise_conv(xt, wt, residual=rt)
+    y.backward(to_dev(dy, dtype).contiguous(memory_format=fmt))
+    ry = orc.pw_fwd(x, w) + r
+    rdx, rdw, _ = orc.pw_bwd(x, w, dy)
+    assert relerr(host(y), ry) < TOL[dtype]
+    assert relerr(host(xt.grad), rdx) < TOL[dtype]
+    assert relerr(host(wt.grad), rdw) < TOL[dtype]
+    assert relerr(host(rt.grad), dy) < 1e-6
+    scale = rs.uniform(0.5, 1.5, Nc).astype(np.float32)
+    shift = rs.uniform(-0.5, 0.5, Nc).astype(np.float32)
+    with torch.no_grad():
+        ya = kdcc.functional.pointwise_conv(xt.detach(), wt.detach(), None, torch.from_numpy(scale).cuda(),
+                                            torch.from_numpy(shift).cuda(), True, residual=rt.detach())
+    ref = np.maximum(orc.pw_fwd(x, w) * scale[None, :, None, None] + shift[None, :, None, None] + r, 0)
+    assert relerr(host(ya), ref) < TOL[dtype]
+
+
 # ---- losses ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("tag", ["kl_T1", "kl_T2", "kl_T5", "kl_big", "kl_cifar_T5"])
