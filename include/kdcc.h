@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KDCC_VERSION 103 /* round 1: layout-aware depthwise/pointwise, confusion matrix, multi-teacher KD, TTA stitch */
+#define KDCC_VERSION 104 /* round 1: layout-aware depthwise/pointwise, confusion matrix, multi-teacher KD, TTA stitch, RAdam */
 
 enum { KDCC_F32 = 0, KDCC_BF16 = 1 };
 enum { KDCC_LAYOUT_NHWC = 0, KDCC_LAYOUT_NCHW = 1 };
@@ -156,6 +156,20 @@ size_t kdcc_colsum_workspace_bytes(long M, int Nc);
 int kdcc_confusion_update(const void *logits, const long long *labels, long long *conf, int N, int C, long HW,
                           long batch_stride, long class_stride, int ignore_index, int dtype,
                           kdcc_stream_t stream);
+
+/* ---- optimizer step of the layerwise loop -------------------------------------------------------------
+ * kdcc_radam_step replaces the per-tensor body of utils/optim/radam.py:41-97 (RAdam, the optimizer of every
+ * cfg/cityscapes/*.json) with one pass:  v = beta2 v + (1-beta2) g^2;  m = beta1 m + (1-beta1) g;  then
+ *   mode 0 (N_sma >= 5):        p += decay * p;  p += step * m / (sqrt(v) + eps)
+ *   mode 1 (degenerated SGD):   p += decay * p;  p += step * m
+ *   mode 2 (step_size < 0):     moments only.
+ * decay = -weight_decay * lr (0: none), step = -step_size * lr with N_sma / step_size computed by the caller as
+ * radam.py:65-84 does (host float64); one_minus_beta* = 1 - beta* evaluated in double by the caller (as the reference
+ * does: 1 - 0.999f in float is off by 1.3e-5 relative).  p, g, m, v fp32 [n], 16-byte aligned; p_lp (nullable)
+ * receives the bf16 copy of the new parameters, i.e. the pointwise GEMM weights of the next step. */
+int kdcc_radam_step(float *p, const float *g, float *m, float *v, void *p_lp, long n, float beta1, float beta2,
+                    float one_minus_beta1, float one_minus_beta2, float eps, float decay, float step, int mode,
+                    kdcc_stream_t stream);
 
 /* ---- sliding-window test-time inference -------------------------------------------
  * kdcc_tta_stitch replaces utils/tta_process.py:39-52 (collect_windows_result) and the np.fliplr of :19-20:

@@ -8,7 +8,7 @@ from . import _abi
 from ._abi import KdccError, LIB_PATH
 from .blocks import DepthwiseSeparableBlock
 from .losses import EnsembleKLDivergenceLoss, KLDivergenceLoss, MSELoss, MultiTeacherKLDivergenceLoss, WeightedHintMSELoss
-from . import checkpoint, functional, tta
+from . import checkpoint, functional, optim, tta
 from .student import DepthwiseStudent
 from .metrics import CityscapesMetricTracker, ConfusionMatrix
 from .trainer import GradBucket, LayerwiseStep

@@ -110,6 +110,9 @@ class HotPathStep:
         self.logits_shape = logits_shape
         self.dlogits = torch.empty(logits_shape, dtype=torch.float32, device=self.device) if (logits_shape and kd_grad) else None
         self.launches_per_step = 0
+        # True once something else keeps flat_lp equal to bf16(flat_params) -- kdcc.optim.RAdam.attach_lp_copy writes it
+        # in the optimizer pass -- so the step does not need its own cast launch (refresh_lp() once before the first step)
+        self.lp_maintained = False
 
     # ---- synthetic inputs of the right shapes (the frozen trunk that would produce them is out of scope) ----
     def make_inputs(self, seed=1, pinned_host=False):
@@ -131,6 +134,11 @@ class HotPathStep:
             ls, lt = rnd(self.logits_shape, torch.float32, 3.0), rnd(self.logits_shape, torch.float32, 3.0)
         return xs, ts, ls, lt
 
+    def refresh_lp(self):
+        """bf16 copy of the whole flat parameter bucket, now (one cast launch)."""
+        if self.code == _abi.BF16:
+            _abi.check(self.L.kdcc_cast_f32_to_bf16(_ptr(self.flat_params), _ptr(self.flat_lp), self.flat_params.numel(), _stream()), "cast")
+
     def _site_weights(self, i):
         a, b, c = self._views[i]
         return self.flat_params[a:b], self.flat_params[b:c], self.flat_grads[a:b], self.flat_grads[b:c]
@@ -144,7 +152,7 @@ class HotPathStep:
         mark = log.mark if log is not None else (lambda name: None)
         launches = 0
         mark("begin")
-        if code == _abi.BF16:
+        if code == _abi.BF16 and not self.lp_maintained:
             chk(L.kdcc_cast_f32_to_bf16(_ptr(self.flat_params), _ptr(self.flat_lp), self.flat_params.numel(), st), "cast")
             mark("cast_w")
             launches += 1

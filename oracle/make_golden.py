@@ -143,6 +143,35 @@ def tta_golden():
     np.savez_compressed(os.path.join(OUT, "tta.npz"), **out)
 
 
+def radam_golden():
+    """utils/optim/radam.py stepped 9 times on seeded parameters / gradients (the first 5 steps take its
+    degenerated-to-SGD branch), with and without weight decay and with degenerated_to_sgd off."""
+    RAdam = _load("ref_radam", "utils/optim/radam.py").RAdam
+    out = {}
+    cfgs = [("plain", dict(lr=5e-3)),                                   # cfg/cityscapes/51M_deeplab_all.json:64-69
+            ("wd", dict(lr=1e-2, weight_decay=1e-2, betas=(0.8, 0.99))),
+            ("nosgd", dict(lr=5e-3, degenerated_to_sgd=False))]
+    for tag, kw in cfgs:
+        torch.manual_seed(5)
+        prm = torch.nn.Parameter(torch.randn(257))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            opt = RAdam([prm], **kw)
+            out[tag + "/p0"] = prm.detach().numpy().copy()
+            grads, ps, ms, vs = [], [], [], []
+            for t in range(9):
+                prm.grad = torch.randn(257) * (1 + t)
+                grads.append(prm.grad.numpy().copy())
+                opt.step()
+                ps.append(prm.detach().numpy().copy())
+                ms.append(opt.state[prm]["exp_avg"].numpy().copy())
+                vs.append(opt.state[prm]["exp_avg_sq"].numpy().copy())
+        out[tag + "/grads"], out[tag + "/p"], out[tag + "/m"], out[tag + "/v"] = map(np.stack, (grads, ps, ms, vs))
+        out[tag + "/hyper"] = np.array([kw.get("lr"), kw.get("betas", (0.9, 0.999))[0], kw.get("betas", (0.9, 0.999))[1],
+                                        1e-8, kw.get("weight_decay", 0.0), float(kw.get("degenerated_to_sgd", True))], np.float64)
+    np.savez_compressed(os.path.join(OUT, "radam.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # deterministic reduction order
@@ -213,7 +242,8 @@ def main():
     metrics_golden()
     ensemble_golden()
     tta_golden()
-    for fn in ("block.npz", "losses.npz", "metrics.npz", "ensemble.npz", "tta.npz"):
+    radam_golden()
+    for fn in ("block.npz", "losses.npz", "metrics.npz", "ensemble.npz", "tta.npz", "radam.npz"):
         print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")
 
 

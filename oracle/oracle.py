@@ -257,3 +257,38 @@ def tta_reverse_mapping(mapping, results, ori_size, count_mode="reference"):
         out.append((tta_resize_bilinear(plain, *ori_size) + tta_resize_bilinear(mirrored, *ori_size)) / 2)
         idx += 2 * n
     return np.stack(out)
+
+
+# ---- optimizer of the layerwise loop (cfg/cityscapes/*.json "optimizer": RAdam) -----------------------------------
+def radam_scalars(step, beta1, beta2, degenerated_to_sgd=True):
+    """(N_sma, step_size) of utils/optim/radam.py:65-84 for the 1-based step count (host scalars, float64)."""
+    import math
+    beta2_t = beta2 ** step
+    n_max = 2 / (1 - beta2) - 1
+    n_sma = n_max - 2 * step * beta2_t / (1 - beta2_t)
+    if n_sma >= 5:
+        size = math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max / (n_max - 2)) / (1 - beta1 ** step)
+    elif degenerated_to_sgd:
+        size = 1.0 / (1 - beta1 ** step)
+    else:
+        size = -1
+    return n_sma, size
+
+
+def radam_step(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, degenerated_to_sgd=True):
+    """One step of utils/optim/radam.py:31-99 on fp32 arrays; `step` is the count AFTER the increment of :63.
+    Returns the new (p, m, v)."""
+    beta1, beta2 = betas
+    p, g, m, v = (np.asarray(a, np.float32) for a in (p, g, m, v))
+    v = (v * np.float32(beta2) + np.float32(1 - beta2) * g * g).astype(np.float32)
+    m = (m * np.float32(beta1) + np.float32(1 - beta1) * g).astype(np.float32)
+    n_sma, size = radam_scalars(step, beta1, beta2, degenerated_to_sgd)
+    if n_sma >= 5:
+        if weight_decay != 0:
+            p = (p + np.float32(-weight_decay * lr) * p).astype(np.float32)
+        p = (p + np.float32(-size * lr) * (m / (np.sqrt(v) + np.float32(eps)))).astype(np.float32)
+    elif size > 0:
+        if weight_decay != 0:
+            p = (p + np.float32(-weight_decay * lr) * p).astype(np.float32)
+        p = (p + np.float32(-size * lr) * m).astype(np.float32)
+    return p, m, v

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(kdcc):
 
 def test_version_and_error_strings(kdcc):
     L = kdcc._abi.lib()
-    assert L.kdcc_version() == 103
+    assert L.kdcc_version() == 104
     assert "success" in kdcc._abi.strerror(0)
     for code in (-1, -2, -3, -4, -5):
         assert kdcc._abi.strerror(code).startswith("kdcc:")
