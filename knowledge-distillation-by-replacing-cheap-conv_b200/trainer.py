@@ -81,3 +81,39 @@ class LayerwiseStep:
             self.bucket.zero()  # == optimizer.zero_grad() for the trainable set, keeps the flat views alive
         return {"loss": loss, "hint_loss": hint_loss, "kd_loss": kd_loss, "supervised_loss": supervised,
                 "teacher_loss": teacher_loss, "output_st": output_st.detach(), "output_tc": output_tc}
+
+
+class ClassificationStep:
+    """Loop body of trainer/classification_trainer.py:24-43 (the CIFAR-10 configs, train_classification.py): the same
+    forward and the same three criterions as the layerwise loop, but the loss that is back-propagated is the KD term
+    (`loss = kd_loss`, :38-39) and the optimizer steps when `(batch_idx + 1) % accumulation_steps == 0` (:41-43 -- not
+    on index 0, unlike the layerwise loop).  Supervised, hint and teacher losses are computed for logging only, as
+    0-dim device tensors (no `.item()` in the step).  Note: this trainer keeps the student in train mode, so its
+    BatchNorm statistics are per rank under data parallelism (the reference runs it on one device)."""
+
+    def __init__(self, model, criterions, optimizer, accumulation_steps=1, process_group=None):
+        self.model, self.criterions, self.optimizer = model, criterions, optimizer
+        self.accumulation_steps = int(accumulation_steps)
+        self.group = process_group
+        self.bucket = GradBucket(model.trainable_parameters())
+
+    def rebuild_bucket(self):
+        self.bucket = GradBucket(self.model.trainable_parameters())
+
+    def __call__(self, data, target, batch_idx):
+        acc = self.accumulation_steps
+        output_st, output_tc = self.model(data)
+        kd_loss = self.criterions[1](output_st, output_tc) / acc
+        with torch.no_grad():  # logged, never back-propagated by this trainer
+            supervised = self.criterions[0](output_st, target) / acc
+            pairs = zip(self.model.student_hidden_outputs, self.model.teacher_hidden_outputs)
+            hint_loss = reduce(lambda a, st: a + self.criterions[2](st[0], st[1]), pairs, torch.zeros((), device=data.device)) / acc
+            teacher_loss = self.criterions[0](output_tc, target)
+        loss = kd_loss
+        loss.backward()
+        if (batch_idx + 1) % acc == 0:
+            self.bucket.all_reduce_mean(self.group)
+            self.optimizer.step()
+            self.bucket.zero()
+        return {"loss": loss, "hint_loss": hint_loss, "kd_loss": kd_loss, "supervised_loss": supervised,
+                "teacher_loss": teacher_loss, "output_st": output_st.detach(), "output_tc": output_tc}

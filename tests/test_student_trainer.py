@@ -168,3 +168,53 @@ def test_layerwise_step_matches_torch_port_on_cpu():
     cm = kdcc.ConfusionMatrix(19, 255, device="cuda")
     cm.update(out["output_st"], target.cuda())
     assert int(cm.mat.sum()) == target.numel()
+
+
+class _PairModel(nn.Module):
+    """Stand-in for a DepthwiseStudent on the CPU: one trainable linear 'student', one frozen 'teacher', one hint pair."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.student, self.teacher = nn.Linear(6, 4), nn.Linear(6, 4)
+        for prm in self.teacher.parameters():
+            prm.requires_grad = False
+        self.student_hidden_outputs, self.teacher_hidden_outputs = [], []
+
+    def trainable_parameters(self):
+        return [prm for prm in self.student.parameters() if prm.requires_grad]
+
+    def forward(self, x):
+        s, t = self.student(x), self.teacher(x)
+        self.student_hidden_outputs, self.teacher_hidden_outputs = [s], [t]
+        return s, t
+
+
+def test_classification_step_backpropagates_kd_only_and_steps_on_the_reference_cadence():
+    """trainer/classification_trainer.py:24-43: loss = kd_loss; step when (batch_idx + 1) % accumulation_steps == 0."""
+    model = _PairModel()
+    crit = [lambda out, tgt: nn.functional.cross_entropy(out, tgt),
+            lambda s, t: ((s - t) ** 2).mean(),          # stands for the KD criterion
+            lambda s, t: (s - t).abs().mean() * 7.0]     # hint criterion: must NOT reach the gradient
+    opt = torch.optim.SGD(model.trainable_parameters(), lr=0.1)
+    step = kdcc.ClassificationStep(model, crit, opt, accumulation_steps=2)
+    torch.manual_seed(4)
+    xs, ys = [torch.randn(5, 6) for _ in range(4)], [torch.randint(0, 4, (5,)) for _ in range(4)]
+    # the same four batches by hand
+    ref = _PairModel()
+    ropt = torch.optim.SGD(ref.trainable_parameters(), lr=0.1)
+    w0 = model.student.weight.detach().clone()
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        out = step(x, y, i)
+        s, t = ref(x)
+        (((s - t) ** 2).mean() / 2).backward()
+        if (i + 1) % 2 == 0:
+            ropt.step()
+            ropt.zero_grad()
+        assert torch.allclose(out["kd_loss"], ((s - t) ** 2).mean() / 2)
+        assert torch.allclose(out["hint_loss"], (s - t).abs().mean() * 7.0 / 2) and not out["hint_loss"].requires_grad
+        assert out["loss"] is out["kd_loss"]
+        if i == 0:
+            assert torch.equal(model.student.weight.detach(), w0)   # no step on index 0 (the layerwise loop would)
+        assert torch.allclose(model.student.weight, ref.student.weight, atol=1e-7)
+    assert not torch.equal(model.student.weight.detach(), w0)
