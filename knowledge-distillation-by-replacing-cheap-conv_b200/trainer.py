@@ -117,3 +117,41 @@ class ClassificationStep:
             self.bucket.zero()
         return {"loss": loss, "hint_loss": hint_loss, "kd_loss": kd_loss, "supervised_loss": supervised,
                 "teacher_loss": teacher_loss, "output_st": output_st.detach(), "output_tc": output_tc}
+
+
+class EnsembleStep:
+    """Loop body of trainer/ensemble_trainer.py:73-90 (multi-teacher distillation, BASELINE config 5): the student is
+    distilled from its own teacher and from `models` (other, frozen, students), with
+        kd = (sum_k WEIGHT * crit_kd(student, model_k(x)) + crit_kd(student, teacher)) / (WEIGHT * K + 1)
+    and `loss = kd + supervised`, both divided by accumulation_steps; step on `(batch_idx + 1) % accumulation_steps`.
+    `kd_multi` (a kdcc.MultiTeacherKLDivergenceLoss) computes the whole KD term in one fused pass -- student logits read
+    once, every teacher once; without it the term is composed from criterions[1] exactly as the reference composes it."""
+
+    def __init__(self, model, models, criterions, optimizer, accumulation_steps=1, weight=1, kd_multi=None, process_group=None):
+        self.model, self.models, self.criterions, self.optimizer = model, list(models), criterions, optimizer
+        self.accumulation_steps, self.weight, self.kd_multi = int(accumulation_steps), weight, kd_multi
+        self.group = process_group
+        self.bucket = GradBucket(model.trainable_parameters())
+
+    def rebuild_bucket(self):
+        self.bucket = GradBucket(self.model.trainable_parameters())
+
+    def __call__(self, data, target, batch_idx):
+        acc = self.accumulation_steps
+        output_st, output_tc = self.model(data)
+        with torch.no_grad():
+            outputs = [m(data) for m in self.models]
+        supervised = self.criterions[0](output_st, target) / acc
+        if self.kd_multi is not None:
+            kd_loss = self.kd_multi(output_st, outputs, output_tc) / acc
+        else:
+            kd_loss = reduce(lambda a, o: a + self.weight * self.criterions[1](output_st, o), outputs, 0)
+            kd_loss = (kd_loss + self.criterions[1](output_st, output_tc)) / (self.weight * len(outputs) + 1) / acc
+        loss = kd_loss + supervised
+        loss.backward()
+        if (batch_idx + 1) % acc == 0:
+            self.bucket.all_reduce_mean(self.group)
+            self.optimizer.step()
+            self.bucket.zero()
+        return {"loss": loss, "kd_loss": kd_loss, "supervised_loss": supervised, "output_st": output_st.detach(),
+                "output_tc": output_tc}

@@ -218,3 +218,33 @@ def test_classification_step_backpropagates_kd_only_and_steps_on_the_reference_c
             assert torch.equal(model.student.weight.detach(), w0)   # no step on index 0 (the layerwise loop would)
         assert torch.allclose(model.student.weight, ref.student.weight, atol=1e-7)
     assert not torch.equal(model.student.weight.detach(), w0)
+
+
+def test_ensemble_step_composes_the_kd_term_like_the_reference():
+    """trainer/ensemble_trainer.py:73-90: kd = (sum_k W * kd(s, m_k(x)) + kd(s, teacher)) / (W * K + 1); loss = kd + sup."""
+    model = _PairModel()
+    torch.manual_seed(9)
+    others = [nn.Linear(6, 4) for _ in range(3)]
+    sup = lambda out, tgt: nn.functional.cross_entropy(out, tgt)
+    kd = lambda s, t: ((s - t) ** 2).mean()
+    opt = torch.optim.SGD(model.trainable_parameters(), lr=0.05)
+    step = kdcc.EnsembleStep(model, others, [sup, kd], opt, accumulation_steps=1, weight=2)
+    ref = _PairModel()
+    ropt = torch.optim.SGD(ref.trainable_parameters(), lr=0.05)
+    for i in range(3):
+        x, y = torch.randn(5, 6), torch.randint(0, 4, (5,))
+        out = step(x, y, i)
+        s, t = ref(x)
+        with torch.no_grad():
+            outs = [m(x) for m in others]
+        want_kd = (sum(2 * kd(s, o) for o in outs) + kd(s, t)) / (2 * 3 + 1)
+        (want_kd + sup(s, y)).backward()
+        ropt.step()
+        ropt.zero_grad()
+        assert torch.allclose(out["kd_loss"], want_kd) and torch.allclose(out["loss"], want_kd + sup(s, y))
+        assert torch.allclose(model.student.weight, ref.student.weight, atol=1e-7)
+    # a fused multi-teacher criterion plugs in with the same call shape
+    calls = []
+    fused = lambda s, outs, t: (calls.append(len(outs)) or sum(kd(s, o) for o in outs) + kd(s, t))
+    kdcc.EnsembleStep(model, others, [sup, kd], opt, kd_multi=fused)(torch.randn(5, 6), torch.randint(0, 4, (5,)), 0)
+    assert calls == [3]
