@@ -68,8 +68,10 @@ struct KdParams {
 };
 
 // CT = compile-time class capacity (values live in registers), EXACT: C == CT so no predicates.
-template <typename T, int CT, bool EXACT, int PIX>
-__global__ void __launch_bounds__(kLossThreads) kd_loss_kernel(const KdParams p) {
+// PROB: targets are probabilities already (EnsembleKLDiv) -- a template parameter so that each form keeps its own,
+// smaller, register footprint (both in one kernel: 170 registers, one block per SM).
+template <typename T, int CT, bool EXACT, int PIX, bool PROB>
+__global__ void __launch_bounds__(kLossThreads, CT <= 19 ? 2 : 1) kd_loss_kernel(const KdParams p) {
   __shared__ float scratch[32];
   const T *__restrict__ sbase = static_cast<const T *>(p.s);
   const T *__restrict__ tbase = static_cast<const T *>(p.t);
@@ -94,38 +96,52 @@ __global__ void __launch_bounds__(kLossThreads) kd_loss_kernel(const KdParams p)
 #pragma unroll
       for (int c = 0; c < CT; ++c)
         if (EXACT || c < C) { smax = fmaxf(smax, sv[c][i]); tmax = fmaxf(tmax, tv[c][i]); }
+      if (!PROB) {
+        // Softmaxed teacher: ONE exponential per logit.  With a = log2-domain student logit, b = teacher logit (both
+        // relative to their max), e_s = 2^a, e_t = 2^b:
+        //   KL (bits) = sum_c p_t (log2 p_t - log2 p_s) = (sum_c e_t (b - a)) / sum e_t - log2 sum e_t + log2 sum e_s
+        //   grad      = gcoef * (e_s / sum e_s - e_t / sum e_t)
+        // (the kernel is otherwise limited by the MUFU pipe: 4 exponentials per logit pair cost 72 us of a 164 us pass)
+        float ssum = 0.f, tsum = 0.f, cross = 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (EXACT || c < C) {
+            const float a = (sv[c][i] - smax) * p.k2, b = (tv[c][i] - tmax) * p.k2;
+            const float es = exp2f(a), et = exp2f(b);
+            ssum += es; tsum += et;
+            if (et > 0.f) cross += et * (b - a);   // p_t == 0 contributes 0 (xlogy), whatever the student says
+            sv[c][i] = es; tv[c][i] = et;
+          }
+        const float rs = 1.f / ssum, rt = 1.f / tsum;
+        local += cross * rt - log2f(tsum) + log2f(ssum);
+        if (dbase != nullptr) {
+#pragma unroll
+          for (int c = 0; c < CT; ++c)
+            if (EXACT || c < C) sv[c][i] = p.gcoef * (sv[c][i] * rs - tv[c][i] * rt);
+        }
+        continue;
+      }
+      // targets are probabilities already (losses/EnsembleKLDiv.py): log-softmax of the student only
       float ssum = 0.f, tsum = 0.f;
 #pragma unroll
       for (int c = 0; c < CT; ++c)
         if (EXACT || c < C) {
           sv[c][i] = (sv[c][i] - smax) * p.k2;  // base-2 exponent relative to the max
           ssum += exp2f(sv[c][i]);
-          if (!p.target_is_prob) {
-            tv[c][i] = (tv[c][i] - tmax) * p.k2;
-            tsum += exp2f(tv[c][i]);
-          } else {
-            tsum += tv[c][i];  // probability mass of the (ensemble) target
-          }
+          tsum += tv[c][i];  // probability mass of the (ensemble) target
         }
       const float ls = log2f(ssum);
-      const float lt = p.target_is_prob ? 0.f : log2f(tsum);
       float kl2 = 0.f;  // KL in bits; converted to nats at finalize
 #pragma unroll
       for (int c = 0; c < CT; ++c)
         if (EXACT || c < C) {
           const float lps = sv[c][i] - ls;  // log2 p_s
           const float ps = exp2f(lps);
-          float pt, lpt;
-          if (!p.target_is_prob) {
-            lpt = tv[c][i] - lt;
-            pt = exp2f(lpt);
-          } else {
-            pt = tv[c][i];
-            lpt = pt > 0.f ? log2f(pt) : 0.f;
-          }
+          const float pt = tv[c][i];
+          const float lpt = pt > 0.f ? log2f(pt) : 0.f;
           if (pt > 0.f) kl2 += pt * (lpt - lps);
-          // gradient: softmax(s/T) * (target mass) - p_t   (mass == 1 for a softmaxed teacher)
-          sv[c][i] = p.gcoef * (p.target_is_prob ? ps * tsum - pt : ps - pt);
+          // gradient: softmax(s/T) * (target mass) - p_t
+          sv[c][i] = p.gcoef * (ps * tsum - pt);
         }
       local += kl2;
     }
@@ -499,8 +515,13 @@ static int launch_kd(const KdParams &p0, bool vec2, int grid_hint, cudaStream_t 
   const int grid = grid_hint;
 #define KD_LAUNCH(CT, EXACT)                                                             \
   do {                                                                                   \
-    if (vec2) kd_loss_kernel<T, CT, EXACT, 2><<<grid, kLossThreads, 0, st>>>(p);         \
-    else kd_loss_kernel<T, CT, EXACT, 1><<<grid, kLossThreads, 0, st>>>(p);              \
+    if (p.target_is_prob) {                                                              \
+      if (vec2) kd_loss_kernel<T, CT, EXACT, 2, true><<<grid, kLossThreads, 0, st>>>(p); \
+      else kd_loss_kernel<T, CT, EXACT, 1, true><<<grid, kLossThreads, 0, st>>>(p);      \
+    } else {                                                                             \
+      if (vec2) kd_loss_kernel<T, CT, EXACT, 2, false><<<grid, kLossThreads, 0, st>>>(p);\
+      else kd_loss_kernel<T, CT, EXACT, 1, false><<<grid, kLossThreads, 0, st>>>(p);     \
+    }                                                                                    \
   } while (0)
   if (C == 19) KD_LAUNCH(19, true);
   else if (C == 10) KD_LAUNCH(10, true);
