@@ -227,22 +227,23 @@ __global__ void __launch_bounds__(kLossThreads) kd_multi_kernel(const KdMultiPar
 #pragma unroll
         for (int c = 0; c < CT; ++c)
           if (EXACT || c < C) tmax = fmaxf(tmax, tv[c][i]);
-        float tsum = 0.f;
+        // one exponential per teacher logit: e = 2^b is kept, sum_c p log2 p = (sum_c e b) / Z - log2 Z, p = e / Z
+        float tsum = 0.f, tb = 0.f;
 #pragma unroll
         for (int c = 0; c < CT; ++c)
           if (EXACT || c < C) {
-            tv[c][i] = (tv[c][i] - tmax) * p.k2;
-            tsum += exp2f(tv[c][i]);
+            const float b = (tv[c][i] - tmax) * p.k2;
+            const float et = exp2f(b);
+            tsum += et;
+            if (et > 0.f) tb += et * b;   // p == 0 contributes 0 (xlogy)
+            tv[c][i] = et;
           }
-        const float lt = log2f(tsum);
+        const float rt = 1.f / tsum;
+        ent[i] += wk * (tb * rt - log2f(tsum));
+        const float wr = wk * rt;
 #pragma unroll
         for (int c = 0; c < CT; ++c)
-          if (EXACT || c < C) {
-            const float lpt = tv[c][i] - lt;
-            const float pt = exp2f(lpt);
-            if (pt > 0.f) ent[i] += wk * pt * lpt;
-            pw[c][i] += wk * pt;
-          }
+          if (EXACT || c < C) pw[c][i] += wr * tv[c][i];
       }
     }
 #pragma unroll
