@@ -34,6 +34,36 @@ struct PlaneWalk {
   }
 };
 
+// One level of a warp-wide reduce-scatter over 2*H values per lane: the lane with bit M set keeps the upper half and
+// hands over the lower one (and vice versa); afterwards a[0..H) holds pair sums and `base` the index of a[0].  Five
+// levels (M = 16 .. 1) leave every lane with the complete sums of its own 1/32 of the values.
+template <int H, int M, int P>
+__device__ __forceinline__ void halve_scatter(float (&a)[P], int lane, int &base) {
+  const bool up = (lane & M) != 0;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const float send = up ? a[i] : a[i + H];
+    const float keep = up ? a[i + H] : a[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+  }
+  if (up) base += H;
+  if constexpr (M > 1) halve_scatter<H / 2, M / 2>(a, lane, base);
+}
+
+// out[u*K+v] = sum over the warp's lanes of acc[u][v] (the k*k tap sums of the rows a warp owns)
+template <int K>
+__device__ __forceinline__ void warp_sum_taps(const float (&acc)[K][K], int lane, float *out) {
+  constexpr int KK = K * K, P = 32 * ((KK + 31) / 32);
+  float a[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) a[i] = i < KK ? acc[i / K][i % K] : 0.f;
+  int base = 0;
+  halve_scatter<P / 2, 16>(a, lane, base);
+#pragma unroll
+  for (int i = 0; i < P / 32; ++i)
+    if (base + i < KK) out[base + i] = a[i];
+}
+
 // CTAs per channel: balance the persistent grid without shredding units into single planes
 static inline int tc_unit_splits(int C, int planes) {
   int best = 1;

@@ -283,14 +283,8 @@ dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         if (lane == 0) ptx::mbar_arrive(t_empty(tb));
       }
       if (cur.last_of_unit()) {
-        // channel (pair) finished: sum the 128 rows -- shuffle inside the warp, fixed order across warps
-#pragma unroll
-        for (int u = 0; u < K; ++u)
-#pragma unroll
-          for (int v = 0; v < K; ++v) {
-            const float r = warp_sum(acc[u][v]);
-            if (lane == 0) red[(grp * 4 + quad) * K * K + u * K + v] = r;
-          }
+        // channel (pair) finished: sum the 128 rows -- reduce-scatter inside the warp, fixed order across warps
+        warp_sum_taps<K>(acc, lane, red + (grp * 4 + quad) * K * K);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int et = threadIdx.x - 64;
         if (et < K * K) {

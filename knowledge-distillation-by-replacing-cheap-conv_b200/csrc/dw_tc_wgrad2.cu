@@ -43,22 +43,6 @@ struct W2Params {
   int dbg;      // KDCC_TC_DEBUG (timing experiments only): 1 skip extraction, 2 skip MMAs, 4 skip transposition
 };
 
-// One level of a warp-wide reduce-scatter over 2*H values per lane: the lane with bit M set keeps the upper half and
-// hands over the lower one (and vice versa); afterwards a[0..H) holds pair sums and `base` the index of a[0].  Five
-// levels (M = 16 .. 1) leave every lane with the complete sums of its own 1/32 of the values.
-template <int H, int M, int P>
-__device__ __forceinline__ void halve_scatter(float (&a)[P], int lane, int &base) {
-  const bool up = (lane & M) != 0;
-#pragma unroll
-  for (int i = 0; i < H; ++i) {
-    const float send = up ? a[i] : a[i + H];
-    const float keep = up ? a[i + H] : a[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
-  }
-  if (up) base += H;
-  if constexpr (M > 1) halve_scatter<H / 2, M / 2>(a, lane, base);
-}
-
 template <int K>
 __global__ void __launch_bounds__(W2_THREADS, 1)
 dw_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy, const W2Params p) {
@@ -249,17 +233,7 @@ dw_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         // channel finished: sum the 128 rows -- inside the warp by recursive halving (each exchange step also halves
         // the number of values a lane is responsible for: 93 shuffles for 81 sums instead of 5 x 81), fixed order
         // across the four warps
-        {
-          constexpr int KK = K * K, P = 32 * ((KK + 31) / 32);
-          float a[P];
-#pragma unroll
-          for (int i = 0; i < P; ++i) a[i] = i < KK ? acc[i / K][i % K] : 0.f;
-          int base = 0;
-          halve_scatter<P / 2, 16>(a, lane, base);
-#pragma unroll
-          for (int i = 0; i < P / 32; ++i)
-            if (base + i < KK) red[(warp - 2) * KK + base + i] = a[i];
-        }
+        warp_sum_taps<K>(acc, lane, red + (warp - 2) * K * K);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int et = threadIdx.x - 64;
         if (et < K * K) {
