@@ -16,14 +16,12 @@ from . import _abi
 
 class RAdam(Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, degenerated_to_sgd=True):
-        if not 0.0 <= lr:
-            raise ValueError("Invalid learning rate: {}".format(lr))
-        if not 0.0 <= eps:
-            raise ValueError("Invalid epsilon value: {}".format(eps))
-        if not 0.0 <= betas[0] < 1.0:
-            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
-        if not 0.0 <= betas[1] < 1.0:
-            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        # same argument checks (ValueError) as radam.py:9-16
+        for ok, what, val in ((lr >= 0.0, "learning rate", lr), (eps >= 0.0, "epsilon value", eps),
+                              (0.0 <= betas[0] < 1.0, "beta parameter at index 0", betas[0]),
+                              (0.0 <= betas[1] < 1.0, "beta parameter at index 1", betas[1])):
+            if not ok:
+                raise ValueError("Invalid %s: %s" % (what, val))
         self.degenerated_to_sgd = degenerated_to_sgd
         # `buffer` only exists so that state_dict()s are interchangeable with the reference's (radam.py:19-24 caches
         # the step scalars there; they are recomputed here, which is a few host flops per tensor)
@@ -39,15 +37,15 @@ class RAdam(Optimizer):
 
     def step_scalars(self, step, beta1, beta2):
         """(N_sma, step_size) of radam.py:65-84 (host float64, as there)."""
-        beta2_t = beta2 ** step
+        decay2 = beta2 ** step
         n_max = 2 / (1 - beta2) - 1
-        n_sma = n_max - 2 * step * beta2_t / (1 - beta2_t)
-        if n_sma >= 5:
-            size = math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max / (n_max - 2)) / (1 - beta1 ** step)
-        elif self.degenerated_to_sgd:
-            size = 1.0 / (1 - beta1 ** step)
+        n_sma = n_max - 2 * step * decay2 / (1 - decay2)
+        bias1 = 1 - beta1 ** step
+        if n_sma >= 5:   # variance rectification term, then Adam's first-moment bias correction
+            rect = (1 - decay2) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max / (n_max - 2)
+            size = math.sqrt(rect) / bias1
         else:
-            size = -1
+            size = 1.0 / bias1 if self.degenerated_to_sgd else -1
         return n_sma, size
 
     @torch.no_grad()
