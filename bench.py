@@ -127,6 +127,21 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------------
 # reference / CPU arm: the reference's own calls (torch CPU backend) restated in oracle/torch_port.py
 # -------------------------------------------------------------------------------------------------------
+def tensor_issue_floor(plan, batch, geom, layout, maps, measured_ms, sm_mhz, sms=148):
+    """What the measured MMA cost model (tools/mma_probe.cu) says the whole-plane tensor-core depthwise
+    backward (dX conv + dW) cannot go below: per 128 x 128 plane 2*d*k MMAs of 43 + 32/2 = 59 clk for the conv and
+    k * 8 MMAs of 10 + 128/2 = 74 clk for the weight gradient, one plane per SM at a time, at the sampled SM clock.
+    Only defined for the geometry those kernels cover; returns None otherwise."""
+    k, d, p = geom
+    if layout != "nchw" or maps > 128 or p % d != 0 or not sm_mhz or not measured_ms:
+        return None
+    planes = batch * sum(ci for ci, _ in plan)
+    clk = planes * (2 * d * k * 59 + k * 8 * 74) / float(sms)
+    floor_ms = clk / (sm_mhz * 1e3)
+    return {"ms": round(floor_ms, 3), "frac": round(floor_ms / measured_ms, 4), "sm_mhz": sm_mhz,
+            "model": "planes x (2*d*k x 59 clk conv + 8*k x 74 clk dW) / %d SMs" % sms}
+
+
 def cpu_reference_image_seconds(plan, maps, geom, budget_s, crop):
     """Seconds the torch-CPU reference path needs for ONE image of the workload, from a bounded sample:
     each distinct site shape is run once (forward, hint MSE, backward) and weighted by its multiplicity,
@@ -394,6 +409,12 @@ def run_kdcc(args, rank, world, local_rank):
                 "frac": dk["frac"], "traffic": traffic, "algorithmic_bytes": alg[dominant][0] if alg[dominant][1] == "B" else None,
                 "peak_source": pk["source"] + (" copy bandwidth" if dk["bound"] == "hbm" else " sustained cuBLAS bf16"),
                 "note": note}
+    try:  # the resource that actually binds the dominant family (an annotation: it must never break the line)
+        if dominant == "dw_bwd" and k >= 7:
+            roofline["tensor_issue_floor"] = tensor_issue_floor(plan, N, (k, d, p), args.layout, maps, dk["ms_per_step"],
+                                                                (clocks or {}).get("sm_mhz"))
+    except Exception:
+        pass
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

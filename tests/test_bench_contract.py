@@ -33,3 +33,15 @@ def test_kdcc_arm_fails_loudly_without_a_gpu():
     r = _run(["--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--e2e-steps", "0"], 300)
     assert r.returncode != 0
     assert "cuda" in (r.stderr + r.stdout).lower()
+
+
+def test_tensor_issue_floor_model():
+    """roofline.tensor_issue_floor: DESIGN.md 4.0's MMA cost model applied to the default workload."""
+    sys.path.insert(0, ROOT)
+    import bench
+    plan = bench.plan_51m()
+    planes = 4 * sum(ci for ci, _ in plan)
+    f = bench.tensor_issue_floor(plan, 4, (9, 5, 20), "nchw", 128, 3.25, 1900.0)
+    assert abs(f["ms"] - planes * (90 * 59 + 72 * 74) / 148 / 1.9e6) < 1e-3 and 0 < f["frac"] < 1
+    assert bench.tensor_issue_floor(plan, 4, (9, 5, 20), "nhwc", 128, 3.25, 1900.0) is None
+    assert bench.tensor_issue_floor(plan, 4, (9, 5, 20), "nchw", 128, 3.25, None) is None
