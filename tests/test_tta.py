@@ -145,3 +145,16 @@ def test_inference_test_runs_student_windows_on_device(golden):
             res = net(windows.cuda()).cpu().numpy()
         want = orc.tta_reverse_mapping(mapping, res, ori).mean(axis=0)
         _same(out[n].cpu().numpy(), want)
+
+
+def test_tta_entry_points_refuse_host_tensors():
+    """No CPU fallback: the stitching kernels are CUDA only and say so."""
+    import torch
+    import kdcc
+    win = torch.zeros(2, 3, 4, 4)
+    coords = torch.zeros(2, 4, dtype=torch.int32)
+    out = torch.zeros(3, 6, 6)
+    with pytest.raises(kdcc.KdccError):
+        kdcc.functional.tta_stitch(win, coords, 6, 6, out)
+    with pytest.raises(kdcc.KdccError):
+        kdcc.functional.resize_bilinear(out, torch.zeros(3, 8, 8))
