@@ -8,11 +8,12 @@
 //    (512 contiguous bytes: fully coalesced), a CTA 6 adjacent column groups x 32 rows; CTAs are persistent (two per
 //    SM, 168 registers each) and walk their tiles with one continuous ring;
 //  * TMA streams the tile row by row (columns j0-1 .. j0+8, out-of-bounds zero fill = the conv padding, so there are
-//    no edge predicates) through an 8-deep shared-memory ring: ~40 KB in flight per CTA independent of registers
-//    (a register-prefetch version with one row in flight per thread reached only 2.4 TB/s);
+//    no edge predicates) through a 16-deep shared-memory ring: ~60 KB in flight per CTA independent of registers
+//    (a register-prefetch version with one row in flight per thread reached only 2.4 TB/s, an 8-deep ring 3.0);
 //  * each thread walks down its column: the input row r is read as three 16-byte LDS (left, centre, right), widened
 //    ONCE to fp32 and scattered into the three output rows it touches (r-1, r, r+1), whose accumulators rotate
-//    through registers; 72 FFMA per arrival, the 9 x 8 taps of the lane's channels stay in registers;
+//    through registers; 72 FMAs per arrival as 36 packed fma.rn.f32x2 (half the issue slots; tools/fma_probe.cu: the
+//    packed form does not raise fp32 throughput), the 9 x 8 taps of the lane's channels stay in registers;
 //  * the input-gradient is the same kernel over dy with mirrored taps;
 //  * weight gradient: same walk, the arriving x row meets the three dy rows around it; 9 x 8 partial sums per
 //    thread over ALL the tiles of a persistent CTA, then a fixed-order shared-memory sum over the CTA's columns and
