@@ -1,6 +1,8 @@
 // Pointwise (1x1) convolution as a dense bf16 GEMM on the sm_100a tensor cores:
 // TMA (128B-swizzled tiles) -> shared memory -> tcgen05.mma with the fp32 accumulator in TMEM ->
-// tcgen05.ld epilogue (BN scale/shift + ReLU, dual output) -> global.
+// tcgen05.ld epilogue -> TMA store of swizzled 32 x 64 tiles (plain bf16 output) or direct 16-byte stores
+// (fp32 split partials; BN scale/shift + ReLU + residual, dual output).  256-wide tiles run as CTA pairs
+// (cta_group::2: each CTA holds half of B, see GemmCfg).
 //
 // Reference semantics: models/students/transform_blocks/depthwise_separable_conv.py:9,13 (nn.Conv2d 1x1)
 // and its autograd backward (dX = dY.W, dW = dY^T.X).
