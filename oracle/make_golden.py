@@ -172,6 +172,24 @@ def radam_golden():
     np.savez_compressed(os.path.join(OUT, "radam.npz"), **out)
 
 
+def ce_golden():
+    """losses/CrossEntropy.py CrossEntropyLoss2d on seeded logits / labels with ignored pixels (the supervised and
+    teacher losses that trainer/layerwise_trainer.py:225,232 evaluates every step for logging)."""
+    CE = _load("ref_ce", "losses/CrossEntropy.py").CrossEntropyLoss2d
+    out = {}
+    torch.manual_seed(41)
+    for i, (n, c, h, w, frac) in enumerate([(2, 19, 17, 23, 0.1), (1, 19, 32, 32, 0.0), (3, 10, 5, 7, 0.5)]):
+        logits = 4 * torch.randn(n, c, h, w)
+        labels = torch.randint(0, c, (n, h, w))
+        labels[torch.rand(n, h, w) < frac] = 255
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            loss = CE(ignore_index=255)(logits, labels)
+        out["c%d/logits" % i], out["c%d/labels" % i] = logits.numpy(), labels.numpy()
+        out["c%d/loss" % i] = np.array(loss.item(), np.float64)
+    np.savez_compressed(os.path.join(OUT, "ce.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # deterministic reduction order
@@ -243,7 +261,8 @@ def main():
     ensemble_golden()
     tta_golden()
     radam_golden()
-    for fn in ("block.npz", "losses.npz", "metrics.npz", "ensemble.npz", "tta.npz", "radam.npz"):
+    ce_golden()
+    for fn in ("block.npz", "losses.npz", "metrics.npz", "ensemble.npz", "tta.npz", "radam.npz", "ce.npz"):
         print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")
 
 

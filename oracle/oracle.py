@@ -292,3 +292,18 @@ def radam_step(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_d
             p = (p + np.float32(-weight_decay * lr) * p).astype(np.float32)
         p = (p + np.float32(-size * lr) * m).astype(np.float32)
     return p, m, v
+
+
+# ---- supervised loss that the layerwise loop logs twice per step (never back-propagated on this path) ------------
+def cross_entropy_2d(logits, target, ignore_index=255):
+    """losses/CrossEntropy.py:10-15 (NLLLoss2d(log_softmax(inputs)), mean over the pixels whose label is not
+    ignore_index; nan when every pixel is ignored, as torch).  logits (N, C, H, W), target (N, H, W) int.  float64."""
+    x = np.asarray(logits, np.float64)
+    t = np.asarray(target).astype(np.int64)
+    m = x.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(x - m).sum(axis=1))
+    valid = t != ignore_index
+    tc = np.where(valid, t, 0)
+    picked = np.take_along_axis(x, tc[:, None], axis=1)[:, 0]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return float(((lse - picked) * valid).sum() / valid.sum())

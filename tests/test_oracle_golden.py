@@ -119,3 +119,14 @@ def test_empty_batch_and_layout_roundtrip():
     L.orc_nhwc_to_nchw(orc._ptr(nhwc), orc._ptr(back), 2, 5, 12)
     assert np.array_equal(a, back)
     assert np.array_equal(nhwc, a.transpose(0, 2, 3, 1))
+
+
+def test_cross_entropy_2d_matches_reference():
+    """losses/CrossEntropy.py (the supervised / teacher losses the layerwise loop logs every step): oracle pinned on the
+    reference module; the CUDA kernel for it is a next-round item, the oracle is ready for it."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ce.npz"))
+    for i in range(3):
+        want = float(g["c%d/loss" % i])
+        assert abs(orc.cross_entropy_2d(g["c%d/logits" % i], g["c%d/labels" % i]) - want) < 1e-6 * abs(want)
+    assert np.isnan(orc.cross_entropy_2d(np.zeros((1, 3, 2, 2), np.float32), np.full((1, 2, 2), 255)))
