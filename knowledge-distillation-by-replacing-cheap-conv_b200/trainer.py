@@ -155,3 +155,46 @@ class EnsembleStep:
             self.bucket.zero()
         return {"loss": loss, "kd_loss": kd_loss, "supervised_loss": supervised, "output_st": output_st.detach(),
                 "output_tc": output_tc}
+
+
+def prepare_train_epoch(model, pruning, epoch, optimizer, make_optimizer, optimizer_args=None, step=None):
+    """Epoch-boundary surgery of trainer/layerwise_trainer.py:78-150 (+ update_optimizer :152-175, create_new_optimizer
+    :177-186) for a kdcc.DepthwiseStudent.  `pruning` is the config's "pruning" section (`pruning_plan`, `hint`,
+    `unfreeze` lists of {"name", "epoch", ...} and `args`, the default block geometry; `pruner` in old checkpoints).
+
+    * epoch 1 with three empty lists: the whole student becomes trainable and gets a fresh optimizer;
+    * an epoch that no list mentions changes nothing;
+    * otherwise the blocks of this epoch are replaced, hooked and unfrozen; epoch 1 builds a NEW optimizer over the
+      trainable student parameters (`make_optimizer(params)`), later epochs add one param group per unfrozen layer
+      with `optimizer_args` (+ the layer's own "lr").  As in the reference the "lr" override is written INTO
+      `optimizer_args` (:171-172), so it also applies to the layers that follow without an "lr" of their own.
+    Returns the optimizer to use from now on; a LayerwiseStep passed as `step` gets it and rebuilds its flat gradient
+    bucket (the trainable set changed)."""
+    plan, hint, unfreeze = pruning['pruning_plan'], pruning['hint'], pruning['unfreeze']
+
+    def done(opt):
+        if step is not None:
+            step.optimizer = opt
+            step.rebuild_bucket()
+        return opt
+
+    if epoch == 1 and len(plan) + len(hint) + len(unfreeze) == 0:
+        for prm in model.student.parameters():
+            prm.requires_grad = True
+        return done(make_optimizer([prm for prm in model.student.parameters() if prm.requires_grad]))
+    if epoch not in [x['epoch'] for x in plan + hint + unfreeze]:
+        return optimizer
+    now = lambda entries: [x for x in entries if x['epoch'] == epoch]
+    kwargs = pruning['args'] if 'args' in pruning else pruning['pruner']
+    model.replace(now(plan), **kwargs)
+    model.register_hint_layers([x['name'] for x in now(hint)])
+    model.unfreeze([x['name'] for x in now(unfreeze)])
+    if epoch == 1:
+        return done(make_optimizer([prm for prm in model.student.parameters() if prm.requires_grad]))
+    optimizer_args = {} if optimizer_args is None else optimizer_args
+    for entry in now(unfreeze):
+        layer = model.get_block(entry['name'], model.student)
+        if 'lr' in entry:
+            optimizer_args['lr'] = entry['lr']
+        optimizer.add_param_group({'params': list(layer.parameters()), **optimizer_args})
+    return done(optimizer)

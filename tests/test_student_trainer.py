@@ -248,3 +248,38 @@ def test_ensemble_step_composes_the_kd_term_like_the_reference():
     fused = lambda s, outs, t: (calls.append(len(outs)) or sum(kd(s, o) for o in outs) + kd(s, t))
     kdcc.EnsembleStep(model, others, [sup, kd], opt, kd_multi=fused)(torch.randn(5, 6), torch.randint(0, 4, (5,)), 0)
     assert calls == [3]
+
+
+def test_prepare_train_epoch_follows_the_reference_schedule():
+    """trainer/layerwise_trainer.py:78-186: surgery only at the epochs the config names, a NEW optimizer at epoch 1,
+    param groups (with the sticky layerwise lr) afterwards, the flat gradient bucket rebuilt with the trainable set."""
+    torch.manual_seed(0)
+    st = kdcc.DepthwiseStudent(TinyTeacher(), {"trainer": {"verbosity": 2}})
+    pruning = {"args": dict(GEOM),
+               "pruning_plan": [{"name": "body.0", "epoch": 1}, {"name": "body.3", "epoch": 3, "args": {"kernel_size": 3, "padding": 2, "dilation": 2}}],
+               "hint": [{"name": "body.0", "epoch": 1}, {"name": "body.3", "epoch": 3}],
+               "unfreeze": [{"name": "body.0", "epoch": 1}, {"name": "body.3", "epoch": 3, "lr": 0.5}, {"name": "head", "epoch": 3}]}
+    made = []
+    make = lambda params: (made.append(len(params)) or torch.optim.SGD(params, lr=0.1))
+    opt_args = {"lr": 0.1}
+    opt = kdcc.prepare_train_epoch(st, pruning, 1, None, make, opt_args)
+    assert made == [2] and st.replaced_block_names == ["body.0"]           # dw + pw weight of the one replaced block
+    assert isinstance(st.get_block("body.0", st.student), kdcc.DepthwiseSeparableBlock)
+    assert isinstance(st.get_block("body.3", st.student), nn.Conv2d)       # not yet
+    step = kdcc.LayerwiseStep(st, [None, None, None], opt)
+    n1 = step.bucket.flat.numel()
+    assert kdcc.prepare_train_epoch(st, pruning, 2, opt, make, opt_args, step=step) is opt and made == [2]   # nothing named at epoch 2
+    assert step.bucket.flat.numel() == n1
+    opt3 = kdcc.prepare_train_epoch(st, pruning, 3, opt, make, opt_args, step=step)
+    assert opt3 is opt and made == [2] and len(opt.param_groups) == 3      # same optimizer, one group per unfrozen layer
+    assert st.replaced_block_names == ["body.0", "body.3"]
+    blk = st.get_block("body.3", st.student)
+    assert blk.separable_conv.dilation == (2, 2)
+    assert opt.param_groups[1]["lr"] == 0.5 and opt.param_groups[2]["lr"] == 0.5   # the override sticks (reference :171-172)
+    assert opt_args["lr"] == 0.5
+    assert step.bucket.flat.numel() == n1 + sum(p.numel() for p in blk.parameters()) + st.get_block("head", st.student).weight.numel()
+    assert len(st.student_hidden_outputs) == 0
+    # a plan with nothing in it: the whole student trains
+    st2 = kdcc.DepthwiseStudent(TinyTeacher(), {"trainer": {"verbosity": 2}})
+    kdcc.prepare_train_epoch(st2, {"args": dict(GEOM), "pruning_plan": [], "hint": [], "unfreeze": []}, 1, None, make)
+    assert all(p.requires_grad for p in st2.student.parameters()) and made[-1] == len(list(st2.student.parameters()))
