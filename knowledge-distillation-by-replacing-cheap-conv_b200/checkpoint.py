@@ -62,22 +62,42 @@ def save_checkpoint(path, model, optimizer, epoch, monitor_best=None, config=Non
     return path
 
 
-def resume(model, optimizer, path, plan_for_epoch, **replace_kwargs):
-    """trainer/layerwise_trainer.py:404-427 for a kdcc.DepthwiseStudent: replay the surgery of every epoch up to the
-    saved one (`plan_for_epoch(i)` -> list of block specs replaced at epoch i), then restore tensors forgivingly.
-    Returns the saved epoch."""
+def resume(model, optimizer, path, make_optimizer, optimizer_args=None, optimizer_type=None, step=None, pruning=None):
+    """trainer/layerwise_trainer.py:404-427 for a kdcc.DepthwiseStudent.
+
+    The saved config's own "pruning" section is replayed through `kdcc.trainer.prepare_train_epoch` for every epoch
+    1..saved epoch -- exactly what the reference does with `self.prepare_train_epoch(i, checkpoint['config'])`: its
+    replace / hint / unfreeze lists are honoured as written, epoch 1 builds a fresh optimizer over the trainable student
+    parameters (`make_optimizer(params)`), later epochs add one param group per unfrozen layer.  The tensors are then
+    restored forgivingly and the optimizer state is loaded unless the optimizer type changed (`optimizer_type`, the
+    current config's optimizer "type", is compared with the checkpoint's; None skips the comparison) -- the only case
+    in which the reference drops it (:420-425).  A state that does not fit the rebuilt param groups raises, as in the
+    reference.  `pruning` overrides the section taken from the checkpoint (a checkpoint whose `config` was not saved);
+    a LayerwiseStep passed as `step` receives the optimizer and rebuilds its gradient bucket.
+    Returns (saved epoch, optimizer, monitor_best)."""
+    from .trainer import prepare_train_epoch
     checkpoint = torch.load(path, map_location=torch.device('cpu'), weights_only=False)
-    for i in range(1, int(checkpoint['epoch']) + 1):
-        blocks = plan_for_epoch(i)
-        if blocks:
-            model.replace(blocks, **replace_kwargs)
-            names = [b['name'] for b in blocks]
-            model.register_hint_layers(names)
-            model.unfreeze(names)
+    epoch = int(checkpoint['epoch'])
+    config = checkpoint.get('config')
+    if pruning is None:
+        if config is None:
+            raise KeyError("checkpoint %s carries no config; pass pruning=" % path)
+        pruning = config['pruning']
+    for i in range(1, epoch + 1):
+        optimizer = prepare_train_epoch(model, pruning, i, optimizer, make_optimizer, optimizer_args, step=step)
     forgiving_state_restore(model, checkpoint['state_dict'])
+    saved_type = None
+    try:
+        saved_type = config['optimizer']['type']
+    except (TypeError, KeyError):
+        pass
     if optimizer is not None and checkpoint.get('optimizer') is not None:
-        try:
+        if optimizer_type is not None and saved_type is not None and saved_type != optimizer_type:
+            logging.warning("optimizer type in %s (%s) differs from the configured one (%s); optimizer state not resumed",
+                            path, saved_type, optimizer_type)
+        else:
             optimizer.load_state_dict(checkpoint['optimizer'])
-        except (ValueError, KeyError):  # optimizer type / parameter groups changed: keep the fresh one (reference :420-425)
-            logging.warning("optimizer state in %s does not fit the current optimizer; not restored", path)
-    return int(checkpoint['epoch'])
+    if step is not None:
+        step.optimizer = optimizer
+        step.rebuild_bucket()
+    return epoch, optimizer, checkpoint.get('monitor_best')

@@ -160,7 +160,7 @@ dw_nhwc3_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const N3Params p
       if (ptile < tiles) pt = n3_tile(p, ptile);
     }
   };
-  if (threadIdx.x == 0 && !(p.dbg & 2))
+  if (threadIdx.x == 0 && !KDCC_DBG(p, 2))
     for (int k = 0; k < p.prefill; ++k) issue_next();
   uint32_t count = 0;  // arrivals consumed
   const uint8_t *mine = smem + jt * px_bytes + vb * N3_VB;   // left neighbour of this thread's column inside a ring row
@@ -173,24 +173,24 @@ dw_nhwc3_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const N3Params p
     // the arriving input row r adds tap row 2 to output row r-1, tap row 1 to r, and starts output row r+1 with tap row 0
     auto arrive = [&](float2 (&prev)[N3_PAIRS], float2 (&cur)[N3_PAIRS], float2 (&next)[N3_PAIRS]) {
       const uint32_t s = count % N3_STAGES;
-      if (!(p.dbg & 2)) {
+      if (!KDCC_DBG(p, 2)) {
         if (threadIdx.x == 0) issue_next();
         ptx::mbar_wait(bars + 8u * s, (count / N3_STAGES) & 1);
       }
       ++count;
       const uint8_t *row = mine + s * row_stride;
       const N3Vec vl = n3_lds(row), vc = n3_lds(row + px_bytes), vr = n3_lds(row + 2 * px_bytes);
-      if (!(p.dbg & 2)) {
+      if (!KDCC_DBG(p, 2)) {
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bars + N3_BAR + 8u * s);
       }
       float2 x[N3_PAIRS];
-      if (p.dbg & 1) {
+      if (KDCC_DBG(p, 1)) {
         unpackv(vl, x);
 #pragma unroll
         for (int e = 0; e < N3_PAIRS; ++e) { prev[e].x += x[e].x + __uint_as_float(vc.w[e]) + __uint_as_float(vr.w[e]); }
         if (skip > 0) { --skip; return; }
-        if (active && !(p.dbg & 4)) n3_stg(optr, prev);
+        if (active && !KDCC_DBG(p, 4)) n3_stg(optr, prev);
         optr += rowp;
         return;
       }
@@ -211,7 +211,7 @@ dw_nhwc3_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const N3Params p
       }
       // `prev` is complete: output row r-1
       if (skip > 0) { --skip; return; }
-      if (active && !(p.dbg & 4)) n3_stg(optr, prev);
+      if (active && !KDCC_DBG(p, 4)) n3_stg(optr, prev);
       optr += rowp;
     };
     float2 a0[N3_PAIRS], a1[N3_PAIRS], a2[N3_PAIRS];
@@ -390,8 +390,7 @@ int dw_nhwc3_conv(const void *in, const float *w, const float *bias, void *out, 
   p.w = w; p.bias = bias; p.N = N; p.H = H; p.W = W; p.C = C; p.flip = flip;
   n3_geometry(p);
   if ((long)N * H * W == 0) return KDCC_OK;
-  const char *dbg = getenv("KDCC_TC_DEBUG");
-  p.dbg = dbg ? atoi(dbg) : 0;
+  p.dbg = tc_debug_bits();
   CUtensorMap tm;
   p.prefill = max(1, N3_STAGES - n3_lag());
   int rc = n3_map(&tm, in, p, N3_WARPS * p.Jb + 2);

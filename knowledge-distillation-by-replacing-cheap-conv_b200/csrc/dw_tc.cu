@@ -195,7 +195,7 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
         const uint32_t acc0 = u ? 1u : 0u;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-          if (t % t_step != t_first || (p.dbg & 2)) continue;
+          if (t % t_step != t_first || KDCC_DBG(p, 2)) continue;
 #pragma unroll
           for (int kk = 0; kk < KS; ++kk)
             tc_mma(d0 + (uint32_t)(t * NT), a_lo + a_off[t][kk], a_hi, b_lo + (uint32_t)(kk * 2 * NT), b_hi, idesc,
@@ -221,7 +221,7 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
       const float *wc = p.w + (long)c * p.k * p.k;
       uint8_t *bs = smem_gen + (b_base - smem_base) + (size_t)s * b_stage_bytes;
       // (tap row u, output column j) pairs; the k taps of a pair land on the band j' = j + v*dil + extra
-      for (int idx = et; idx < ((p.dbg & 1) ? 0 : p.k * NT); idx += 128) {
+      for (int idx = et; idx < (KDCC_DBG(p, 1) ? 0 : p.k * NT); idx += 128) {
         const int u = idx / NT, j = idx % NT;
         const float *wr = wc + (p.flip ? (p.k - 1 - u) * p.k : u * p.k);
         uint8_t *row = bs + u * BU_BYTES + j * 16;
@@ -262,7 +262,7 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
         uint32_t vr[32];
         ptx::tmem_ld_32x32b_x32(t_row + ch * 32, vr);
         ptx::tmem_ld_wait();
-        if (gi < p.Ho && !(p.dbg & 4)) {
+        if (gi < p.Ho && !KDCC_DBG(p, 4)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = j0 + ch * 32 + q * 8;
@@ -354,8 +354,7 @@ int dw_tc_conv(const void *in, const float *w, const float *bias, void *out, int
   p.w = w; p.bias = bias;
   p.out = static_cast<__nv_bfloat16 *>(out);
   if (p.planes == 0 || C == 0) return KDCC_OK;
-  const char *dbg = getenv("KDCC_TC_DEBUG");
-  p.dbg = dbg ? atoi(dbg) : 0;
+  p.dbg = tc_debug_bits();
   p.extra = tc_extra(pad);
   const char *is = getenv("KDCC_DW_TC_ISSUERS");
   p.issuers = is ? max(1, min(4, atoi(is))) : 4;

@@ -140,7 +140,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         const uint32_t a_base = (((smem_base + xp_off + s * xp_bytes) & 0x3FFFF) >> 4) | a_lbo;
         const uint32_t b_base = (((smem_base + tz_off + (unit & 1) * tz_bytes) & 0x3FFFF) >> 4) | b_lbo;
         const uint32_t d0 = tmem_base + (uint32_t)s * 256u;
-        if (!(p.dbg & 2)) {
+        if (!KDCC_DBG(p, 2)) {
 #pragma unroll 1
           for (int u = 0; u < p.k; ++u) {
             const uint32_t a_u = a_base + (uint32_t)(u * p.dil);       // tap row u: u*d rows of 16 bytes further down
@@ -174,7 +174,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       const float *wc = p.w + (long)c * p.k * p.k;
       uint8_t *ts = smem_gen + tz_off + (size_t)s * tz_bytes;
       // (tap row u, output phase-column q): tap v sits at reduction index q' = q - p/d + v
-      for (int idx = r; idx < ((p.dbg & 1) ? 0 : p.k * 32); idx += 128) {
+      for (int idx = r; idx < (KDCC_DBG(p, 1) ? 0 : p.k * 32); idx += 128) {
         const int u = idx >> 5, q = idx & 31;
         const float *wr = wc + (p.flip ? (p.k - 1 - u) * p.k : u * p.k);
         float wv[9];
@@ -215,7 +215,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       ptx::mbar_wait(stg_full(s), ph);
       const uint8_t *stg = smem_gen + s * C2_STG;
       uint8_t *xp = smem_gen + xp_off + (size_t)s * xp_bytes + (size_t)(r + p.pad) * 16;
-      if (!(p.dbg & 8)) {
+      if (!KDCC_DBG(p, 8)) {
 #pragma unroll 1
         for (int g = 0; g * D < nchunks; ++g) {
           // 8*D consecutive columns of row r -> 8 phase-columns (one 16-byte chunk) of each of the D phases
@@ -291,7 +291,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && !(p.dbg & 4)) {
+        if (lane == 0 && !KDCC_DBG(p, 4)) {
           ptx::tma_store_4d(&tm_out, smem_base + tile, 8 * D * g0, 32 * quad, c, w.pl);
           ptx::tma_store_commit();
         }
@@ -372,8 +372,7 @@ int dw_tc_conv2(const void *in, const float *w, const float *bias, void *out, in
   p.w = w; p.bias = bias;
   p.out = static_cast<__nv_bfloat16 *>(out);
   if (N == 0 || C == 0) return KDCC_OK;
-  const char *dbg = getenv("KDCC_TC_DEBUG");
-  p.dbg = dbg ? atoi(dbg) : 0;
+  p.dbg = tc_debug_bits();
   // compile-time MMA schedules for the shapes that matter; every other supported shape takes the run-time loops
   if (dil == 5 && p.nt == 1 && p.ks == 2) return conv2_launch<5, 1, 2>(in, p, st);  // Cityscapes: 9x9, dilation 5, 128 columns
   if (dil == 1 && p.nt == 4 && p.ks == 3) return conv2_launch<1, 4, 3>(in, p, st);  // 3x3 on a 128-column plane

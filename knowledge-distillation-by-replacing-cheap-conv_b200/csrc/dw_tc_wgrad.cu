@@ -194,7 +194,7 @@ dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         // single window: tap row u starts u*dil rows (128 B each) further down the same tile
         const uint32_t xa = smem_base + xs * x_bytes + (p.single ? (uint32_t)(u * p.dil) * 128u : 0u);
         const uint32_t b_lo = ((xa & 0x3FFFF) >> 4) | ((uint32_t)(p.box_bytes >> 4) << 16);
-        if (!(p.dbg & 2)) {
+        if (!KDCC_DBG(p, 2)) {
 #pragma unroll
           for (int ks = 0; ks < WG_TILE / 16; ++ks)  // 16 reduction rows per MMA: 8 TMEM columns of A, 2 KB of B
             wg_mma_ts(d_tmem, a_tmem + ks * 8, b_lo + ks * 128, b_hi, idesc, ks ? 1u : 0u);
@@ -263,7 +263,7 @@ dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         ptx::mbar_wait(t_full(tb), (tit >> 1) & 1);
         ptx::tcgen05_fence_after();
         const uint32_t t_row = tmem_base + (tb ? WG_TMEM_D1 : 0u) + ((uint32_t)(quad * 32) << 16);
-        for (int c3 = 0; c3 < ((p.dbg & 1) ? 0 : nch); ++c3) {
+        for (int c3 = 0; c3 < (KDCC_DBG(p, 1) ? 0 : nch); ++c3) {
           const int col0 = 32 * (quad + c3);
           if (col0 >= p.nq) break;
           uint32_t vr[32];
@@ -360,8 +360,7 @@ int dw_tc_wgrad(const void *x, const void *dy, float *dw, float *part, int N, in
   DwTcWgradParams p{};
   p.N = N; p.C = C; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.k = k; p.dil = dil; p.pad = pad;
   p.halo = dil * (k - 1);
-  const char *dbg = getenv("KDCC_TC_DEBUG");
-  p.dbg = dbg ? atoi(dbg) : 0;
+  p.dbg = tc_debug_bits();
   p.extra = (8 - pad % 8) % 8;
   p.nq = (WG_TILE + p.halo + p.extra + 15) / 16 * 16;
   p.nbox = ceil_div(p.nq, 64);

@@ -131,7 +131,7 @@ dw_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           ptx::mbar_wait(t_empty(tb), ((tit >> 1) & 1) ^ 1);
           ptx::tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + W2_TMEM_P + (uint32_t)tb * 128u;
-          if (!(p.dbg & 2)) {
+          if (!KDCC_DBG(p, 2)) {
             for (int pl = 0; pl < np; ++pl) {
               // tap row u: the B window starts u*d - p rows from the plane's first row, inside the zero gap if negative
               const uint32_t xa = smem_base + s * W2_STAGE + (uint32_t)(W2_GAP + pl * W2_SLOT + u * p.dil - p.pad) * 128u;
@@ -173,7 +173,7 @@ dw_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
               const int r = half * 64 + 2 * q;  // TMEM column r/2 = (dy[r][j], dy[r+1][j])
               const uint32_t lo = *reinterpret_cast<const uint16_t *>(tile + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
               const uint32_t hi = *reinterpret_cast<const uint16_t *>(tile + (r + 1) * 128 + ((chunk ^ ((r + 1) & 7)) << 4) + within);
-              regs[q] = (p.dbg & 4) ? 0u : (lo | (hi << 16));
+              regs[q] = KDCC_DBG(p, 4) ? 0u : (lo | (hi << 16));
             }
             ptx::tmem_st_32x32b_x32(t_dst + half * 32, regs);
           }
@@ -211,7 +211,7 @@ dw_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         ptx::mbar_wait(t_full(tb), (tit >> 1) & 1);
         ptx::tcgen05_fence_after();
         const uint32_t t_row = tmem_base + W2_TMEM_P + (uint32_t)tb * 128u + ((uint32_t)(quad * 32) << 16);
-        for (int col0 = c_first; col0 <= c_last && !(p.dbg & 1); col0 += 32) {
+        for (int col0 = c_first; col0 <= c_last && !KDCC_DBG(p, 1); col0 += 32) {
           if (col0 < 0 || col0 >= 128) continue;
           uint32_t vr[32];
           ptx::tmem_ld_32x32b_x32(t_row + col0, vr);
@@ -305,8 +305,7 @@ int dw_tc_wgrad2(const void *x, const void *dy, float *dw, float *part, int N, i
   p.npairs = (N + 1) / 2;
   p.splits = w2_splits(N, C);
   p.units = (long)C * p.splits;
-  const char *dbg = getenv("KDCC_TC_DEBUG");
-  p.dbg = dbg ? atoi(dbg) : 0;
+  p.dbg = tc_debug_bits();
   switch (k) {
     case 1: return wgrad2_launch<1>(x, dy, dw, part, p, st);
     case 3: return wgrad2_launch<3>(x, dy, dw, part, p, st);

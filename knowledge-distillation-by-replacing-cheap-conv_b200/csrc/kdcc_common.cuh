@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/kdcc.h"
 
@@ -154,5 +155,20 @@ __device__ __forceinline__ float block_sum(float v, float *scratch) {
   __syncthreads();
   return r;
 }
+
+// ---- stage-skipping switches of the timing experiments (tools/gpu_nhwc3_probe.sh) --------------------
+// They make kernels skip MMAs / stores, i.e. produce WRONG results on purpose, so the shipped library does not contain
+// them: without -DKDCC_DEBUG every test is the constant `false` (the branches fold away) and KDCC_TC_DEBUG in the
+// environment is ignored.  tools/build_variant.sh builds an instrumented copy with -DKDCC_DEBUG.
+#ifdef KDCC_DEBUG
+#define KDCC_DBG(p, bit) (((p).dbg & (bit)) != 0)
+static inline int tc_debug_bits() {
+  const char *e = getenv("KDCC_TC_DEBUG");
+  return e ? atoi(e) : 0;
+}
+#else
+#define KDCC_DBG(p, bit) false
+static inline int tc_debug_bits() { return 0; }
+#endif
 
 }  // namespace kdcc

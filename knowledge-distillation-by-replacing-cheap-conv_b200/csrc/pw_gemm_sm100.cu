@@ -479,12 +479,22 @@ int pw_sm100_bwd_dx(const void *dy, const void *w, void *dx, long M, int K, int 
 
 static int dw_bj(int K) { return (K >= 256 && K % 256 == 0) ? 256 : (K > 64 ? 128 : 64); }
 
+// Splits of the weight-gradient reduction: one reduction block (64 pixels, never across images in the NCHW form) is
+// the unit, every split owns at least one.  `rblocks` differs by layout -- ceil(M / 64) for NHWC, batch * ceil(P / 64) for
+// NCHW -- so the launch and the workspace bound below share this one formula.
+static int dw_splits_for(long rblocks, int K, int Nc) {
+  const long tiles = (long)ceil_div(Nc, GEMM_BI) * ceil_div(K, dw_bj(K));
+  const long s = min(max(1L, (long)kNumSMs / tiles), rblocks);
+  const long per = ceil_div<long>(rblocks, s);
+  return (int)ceil_div<long>(rblocks, per);
+}
+
+// Upper bound on the split count for either layout and any batch (what kdcc_pw_bwd_workspace_bytes sizes for): the
+// split count never exceeds kNumSMs / tiles, nor the number of reduction blocks, of which there are at most M / 8
+// (an image contributes at least one block and at least 8 pixels).
 int pw_sm100_dw_splits(long M, int K, int Nc) {
   const long tiles = (long)ceil_div(Nc, GEMM_BI) * ceil_div(K, dw_bj(K));
-  const long rblocks = ceil_div<long>(M, GEMM_BR);
-  long s = min(max(1L, (long)kNumSMs / tiles), rblocks);
-  const long per = ceil_div<long>(rblocks, s);
-  return (int)ceil_div<long>(rblocks, per);  // every split owns at least one reduction block
+  return (int)min(max(1L, (long)kNumSMs / tiles), max(1L, ceil_div<long>(M, 8)));
 }
 
 int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long M, int K, int Nc, int batch, int layout,
@@ -495,7 +505,8 @@ int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long 
   int rc;
   if (layout == KDCC_LAYOUT_NHWC) {
     p.R = (int)M; p.batch = 1;
-    p.splits = pw_sm100_dw_splits(M, K, Nc);
+    p.splits = dw_splits_for(ceil_div<long>(M, GEMM_BR), K, Nc);
+    if (p.splits > pw_sm100_dw_splits(M, K, Nc)) return KDCC_EWORKSPACE;
     p.out_f32 = p.splits == 1 ? dw : part;
     rc = gemm_dispatch_bj<true, true>(dy, x, p, st);   // both operands are MN-major views
   } else {
@@ -503,11 +514,8 @@ int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long 
     // reduction runs over (image, pixel block)
     const int P = (int)(M / batch);
     p.R = P; p.batch = batch; p.a_batched = 1; p.b_batched = 1; p.r_spans_batch = 1;
-    const long rblocks = (long)batch * ceil_div(P, GEMM_BR);
-    const long tiles = (long)ceil_div(Nc, GEMM_BI) * ceil_div(K, dw_bj(K));
-    long s = min(max(1L, (long)kNumSMs / tiles), rblocks);
-    const long per = ceil_div<long>(rblocks, s);
-    p.splits = (int)ceil_div<long>(rblocks, per);
+    p.splits = dw_splits_for((long)batch * ceil_div(P, GEMM_BR), K, Nc);
+    if (p.splits > pw_sm100_dw_splits(M, K, Nc)) return KDCC_EWORKSPACE;  // the caller's workspace is sized by that bound
     p.out_f32 = p.splits == 1 ? dw : part;
     rc = gemm_dispatch_bj<false, false>(dy, x, p, st);
   }

@@ -35,6 +35,24 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _device_guard(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current: kernels, TMA descriptors, function attributes
+    and `_stream()` belong to the device the tensors live on, which need not be the current one (a process driving
+    several devices, a model moved by hand).  Costs one `current_device()` query when the devices already agree."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapped
+
+
 def _ptr(t):
     return t.data_ptr() if t is not None else None
 
@@ -67,6 +85,7 @@ def _empty_like_layout(n, c, h, w, like, layout):
     return _empty_nhwc(n, c, h, w, like)
 
 
+@_device_guard
 def cast_weight(w_f32, dtype):
     """fp32 master parameter -> activation dtype through kdcc_cast_f32_to_bf16 (no torch arithmetic)."""
     if dtype == torch.float32:
@@ -82,6 +101,7 @@ def cast_weight(w_f32, dtype):
 # ---------------------------------------------------------------------------------------------------
 class _DepthwiseConv(torch.autograd.Function):
     @staticmethod
+    @_device_guard
     def forward(ctx, x, weight, bias, k, dil, pad):
         _require_cuda(x, weight, bias)
         N, C, H, W = x.shape
@@ -103,6 +123,7 @@ class _DepthwiseConv(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_device_guard
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         k, dil, pad, has_bias, wshape, layout = ctx.geom
@@ -130,6 +151,7 @@ def depthwise_conv(x, weight, bias, kernel_size, dilation, padding):
 # ---------------------------------------------------------------------------------------------------
 class _PointwiseConv(torch.autograd.Function):
     @staticmethod
+    @_device_guard
     def forward(ctx, x, weight, bias, scale, shift, relu, residual=None):
         _require_cuda(x, weight, bias)
         N, K, H, W = x.shape
@@ -167,6 +189,7 @@ class _PointwiseConv(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_device_guard
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         has_bias, wshape, layout = ctx.meta
@@ -207,6 +230,19 @@ def pointwise_conv(x, weight, bias=None, scale=None, shift=None, relu=False, res
 # ---------------------------------------------------------------------------------------------------
 # losses
 # ---------------------------------------------------------------------------------------------------
+def _take_grad(ctx):
+    """The loss kernels emit d loss / d input in the forward pass; backward scales that buffer in place and hands it
+    out, so it can be consumed once.  A second backward through the same node (retain_graph=True, or one loss tensor
+    used in two graphs) raises instead of silently returning no gradient."""
+    if getattr(ctx, "consumed", False):
+        raise _abi.KdccError("this kdcc loss was already back-propagated; its fused gradient buffer is consumed by the first "
+                             "backward -- call the criterion again instead of backward(retain_graph=True)")
+    ds = ctx.ds
+    ctx.ds = None
+    ctx.consumed = ds is not None
+    return ds
+
+
 def _logit_strides(t):
     """(N, C, HW, batch_stride, class_stride, pixel_stride) of a (N,C,*spatial) tensor, or None."""
     N, C = t.shape[0], t.shape[1]
@@ -222,6 +258,7 @@ def _logit_strides(t):
 
 class _KdLoss(torch.autograd.Function):
     @staticmethod
+    @_device_guard
     def forward(ctx, s, t, temperature, target_is_prob):
         _require_cuda(s, t)
         if s.shape != t.shape or s.dim() < 2:
@@ -247,14 +284,14 @@ class _KdLoss(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_device_guard
     def backward(ctx, g):
-        ds = ctx.ds
+        ds = _take_grad(ctx)
         if ds is None:
             return None, None, None, None
         g = g.detach().float().contiguous()
         _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
                    "kdcc_scale_inplace")
-        ctx.ds = None
         return ds, None, None, None
 
 
@@ -265,6 +302,7 @@ def kd_loss(inputs, targets, temperature=1.0, target_is_prob=False):
 
 class _KdLossMulti(torch.autograd.Function):
     @staticmethod
+    @_device_guard
     def forward(ctx, s, temperature, weights, *teachers):
         import ctypes
         _require_cuda(s, *teachers)
@@ -296,14 +334,14 @@ class _KdLossMulti(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_device_guard
     def backward(ctx, g):
-        ds = ctx.ds
+        ds = _take_grad(ctx)
         if ds is None:
             return (None,) * (3 + ctx.K)
         g = g.detach().float().contiguous()
         _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
                    "kdcc_scale_inplace")
-        ctx.ds = None
         return (ds,) + (None,) * (2 + ctx.K)
 
 
@@ -316,6 +354,7 @@ def kd_loss_multi(inputs, teachers, weights, temperature=1.0):
 
 class _HintLoss(torch.autograd.Function):
     @staticmethod
+    @_device_guard
     def forward(ctx, s, t, weight, scale):
         _require_cuda(s, t, weight)
         if s.shape != t.shape or s.dim() < 2:
@@ -349,14 +388,14 @@ class _HintLoss(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_device_guard
     def backward(ctx, g):
-        ds = ctx.ds
+        ds = _take_grad(ctx)
         if ds is None:
             return None, None, None, None
         g = g.detach().float().contiguous()
         _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
                    "kdcc_scale_inplace")
-        ctx.ds = None
         return ds, None, None, None
 
 
@@ -369,6 +408,7 @@ def hint_loss(inputs, targets, filter_weight=None, scale=1.0):
 # segmentation metric
 # ---------------------------------------------------------------------------------------------------
 @torch.no_grad()
+@_device_guard
 def confusion_update(conf, logits, target, ignore_index=255):
     """conf (C*C int64, device) += confusion matrix of argmax(logits, 1) against target -- utils/util.py:108-128.
     One kernel pass over the logits and labels; nothing is copied to the host."""
@@ -398,6 +438,7 @@ _COUNT_MODES = {"reference": 0, "coverage": 1}
 
 
 @torch.no_grad()
+@_device_guard
 def tta_stitch(windows, coords, h, w, out, flip=False, count_mode="reference", alpha=1.0, accumulate=False):
     """out (C, h, w) fp32 (+)= alpha * overlap-add of `windows` (n, C, th, tw) placed at `coords` (n, 4) int32 device
     tensor of (x1, y1, x2, y2), divided by the window counter -- utils/tta_process.py:39-52; flip=True un-mirrors the
@@ -418,6 +459,7 @@ def tta_stitch(windows, coords, h, w, out, flip=False, count_mode="reference", a
 
 
 @torch.no_grad()
+@_device_guard
 def resize_bilinear(src, out, alpha=1.0, accumulate=False):
     """out (C, H, W) (+)= alpha * cv2.INTER_LINEAR resize of every plane of src (C, h, w) -- utils/tta_process.py:29-36."""
     _require_cuda(src, out)

@@ -23,19 +23,27 @@ class GradBucket:
     """Flat fp32 view of the trainable parameters' gradients: one all-reduce per optimizer step.
     Rebuild it (`GradBucket(params)`) whenever prepare_train_epoch changes the trainable set."""
 
+    ALIGN = 32  # floats
+
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        # every gradient starts on a 128-byte boundary of the bucket (32 floats): the fused optimizer and the GEMM
+        # epilogues use 16-byte accesses, and a 19-element classifier bias must not misalign whatever follows it
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += -(-p.numel() // self.ALIGN) * self.ALIGN
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:  # parameters' .grad become views into the bucket: no copies at step time
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):  # .grad become views into the bucket: no copies at step time
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
 
     def zero(self):
         self.flat.zero_()
+
+    def dense(self):
+        """The gradients back to back without the alignment padding (a copy; for tests and logging)."""
+        return torch.cat([self.flat[o:o + p.numel()] for p, o in zip(self.params, self.offsets)]) if self.params else self.flat
 
     def all_reduce_mean(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -167,7 +175,8 @@ def prepare_train_epoch(model, pruning, epoch, optimizer, make_optimizer, optimi
     * otherwise the blocks of this epoch are replaced, hooked and unfrozen; epoch 1 builds a NEW optimizer over the
       trainable student parameters (`make_optimizer(params)`), later epochs add one param group per unfrozen layer
       with `optimizer_args` (+ the layer's own "lr").  As in the reference the "lr" override is written INTO
-      `optimizer_args` (:171-172), so it also applies to the layers that follow without an "lr" of their own.
+      `optimizer_args` (:171-172), so it also applies to the layers that follow without an "lr" of their own (pass
+      the config's optimizer "args" dict; with None the dict is kept on the model so the override still persists).
     Returns the optimizer to use from now on; a LayerwiseStep passed as `step` gets it and rebuilds its flat gradient
     bucket (the trainable set changed)."""
     plan, hint, unfreeze = pruning['pruning_plan'], pruning['hint'], pruning['unfreeze']
@@ -191,7 +200,10 @@ def prepare_train_epoch(model, pruning, epoch, optimizer, make_optimizer, optimi
     model.unfreeze([x['name'] for x in now(unfreeze)])
     if epoch == 1:
         return done(make_optimizer([prm for prm in model.student.parameters() if prm.requires_grad]))
-    optimizer_args = {} if optimizer_args is None else optimizer_args
+    if optimizer_args is None:
+        # the reference mutates config['optimizer']['args'] itself, so an "lr" override outlives the epoch; without a
+        # caller-owned dict the same persistence is kept on the model
+        optimizer_args = model.__dict__.setdefault('_kdcc_optimizer_args', {})
     for entry in now(unfreeze):
         layer = model.get_block(entry['name'], model.student)
         if 'lr' in entry:

@@ -190,9 +190,25 @@ def ce_golden():
     np.savez_compressed(os.path.join(OUT, "ce.npz"), **out)
 
 
+def block_extra_golden():
+    """Round 2: Cityscapes-geometry cases the NCHW tensor-core kernels accept (W % 8 == 0), so that path is compared
+    with the reference's own fp32 block -- taps NOT pre-rounded to bf16 -- and one full 128 x 128 plane.
+        python oracle/make_golden.py extra"""
+    Block = _load("ref_dsc", "models/students/transform_blocks/depthwise_separable_conv.py").DepthwiseSeparableBlock
+    blocks = {}
+    #                 tag              N  Ci  Co    H    W  k  d   p  seed
+    for spec in [("city_k9d5_w32",     2, 16, 24,  40,  32, 9, 5, 20, 17),   # small planes, image pair
+                 ("city_k9d5_plane",   1,  8,  8, 128, 128, 9, 5, 20, 18)]:  # a whole 128 x 128 plane (1024^2 crop)
+        blocks.update(block_case(Block, *spec))
+    np.savez_compressed(os.path.join(OUT, "block_extra.npz"), **blocks)
+    print("block_extra.npz", os.path.getsize(os.path.join(OUT, "block_extra.npz")), "bytes")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # deterministic reduction order
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        return block_extra_golden()
     blockmod = _load("ref_dsc", "models/students/transform_blocks/depthwise_separable_conv.py")
     Block = blockmod.DepthwiseSeparableBlock
     kl = _load("ref_kl", "losses/KLDiv.py").KLDivergenceLoss

@@ -21,18 +21,64 @@ def test_checkpoint_dict_has_the_reference_keys(tmp_path):
     assert os.path.exists(tmp_path / "model_best.pth")
 
 
+def _pruning(two_epochs=False):
+    """The config's "pruning" section (cfg/cityscapes/*.json): plan / hint / unfreeze lists with epochs + default args."""
+    plan = [dict(b) for b in PLAN]
+    if two_epochs:
+        plan[1]["epoch"] = 2
+    names = [{"name": b["name"], "epoch": b["epoch"]} for b in plan]
+    unfreeze = [dict(n) for n in names]
+    if two_epochs:
+        unfreeze[1]["lr"] = 0.02      # per-layer learning rate (layerwise_trainer.py:171-172)
+    return {"pruning_plan": plan, "hint": names, "unfreeze": unfreeze, "args": dict(GEOM)}
+
+
 def test_resume_replays_surgery_then_restores(tmp_path):
     st = make_student()
     with torch.no_grad():
         for p in st.trainable_parameters():
             p.add_(1.0)
-    path = ck.save_checkpoint(str(tmp_path / "c.pth"), st, None, epoch=1)
+    path = ck.save_checkpoint(str(tmp_path / "c.pth"), st, None, epoch=1, config={"pruning": _pruning(), "optimizer": {"type": "SGD"}})
     torch.manual_seed(0)
     fresh = kdcc.DepthwiseStudent(TinyTeacher(), {"trainer": {"verbosity": 2}})   # un-operated student: teacher-shaped
-    epoch = ck.resume(fresh, None, path, lambda i: [b for b in PLAN if b["epoch"] == i], **GEOM)
-    assert epoch == 1 and fresh.replaced_block_names == st.replaced_block_names
+    epoch, opt, best = ck.resume(fresh, None, path, lambda ps: torch.optim.SGD(ps, lr=0.1))
+    assert epoch == 1 and best is None and fresh.replaced_block_names == st.replaced_block_names
+    assert len(opt.param_groups) == 1 and len(opt.param_groups[0]["params"]) == 4   # fresh optimizer of epoch 1
     for (k, a), (_, b) in zip(st.state_dict().items(), fresh.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_resume_rebuilds_param_groups_and_restores_the_optimizer_state(tmp_path):
+    """A two-epoch plan: epoch 1 creates the optimizer, epoch 2 adds a param group with its own lr.  The reference
+    replays prepare_train_epoch for every saved epoch so that optimizer.load_state_dict fits (layerwise_trainer.py:
+    413-427); the RAdam moments must come back, and a changed optimizer type must leave the fresh state alone."""
+    from kdcc.trainer import prepare_train_epoch
+    pruning = _pruning(two_epochs=True)
+    make = lambda ps: kdcc.optim.RAdam(ps, lr=0.1)
+    torch.manual_seed(0)
+    st = kdcc.DepthwiseStudent(TinyTeacher(), {"trainer": {"verbosity": 2}})
+    args = {"lr": 0.1}
+    opt = None
+    for ep in (1, 2):
+        opt = prepare_train_epoch(st, pruning, ep, opt, make, args)
+    assert [len(g["params"]) for g in opt.param_groups] == [2, 2] and opt.param_groups[1]["lr"] == 0.02
+    for i, p in enumerate(st.trainable_parameters()):       # hand-made optimizer state: resume must bring it back
+        opt.state[p] = {"step": 3, "exp_avg": torch.full_like(p, float(i + 1)), "exp_avg_sq": torch.full_like(p, 0.5)}
+    path = ck.save_checkpoint(str(tmp_path / "c2.pth"), st, opt, epoch=2, monitor_best=0.25,
+                              config={"pruning": pruning, "optimizer": {"type": "RAdam", "args": {"lr": 0.1}}})
+
+    torch.manual_seed(0)
+    fresh = kdcc.DepthwiseStudent(TinyTeacher(), {"trainer": {"verbosity": 2}})
+    epoch, ropt, best = ck.resume(fresh, None, path, make, optimizer_args={"lr": 0.1}, optimizer_type="RAdam")
+    assert (epoch, best) == (2, 0.25) and fresh.replaced_block_names == ["body.0", "body.3"]
+    assert [len(g["params"]) for g in ropt.param_groups] == [2, 2] and ropt.param_groups[1]["lr"] == 0.02
+    for i, p in enumerate(fresh.trainable_parameters()):
+        assert ropt.state[p]["step"] == 3 and float(ropt.state[p]["exp_avg"].mean()) == float(i + 1)
+
+    torch.manual_seed(0)
+    other = kdcc.DepthwiseStudent(TinyTeacher(), {"trainer": {"verbosity": 2}})
+    _, sopt, _ = ck.resume(other, None, path, lambda ps: torch.optim.SGD(ps, lr=0.1), optimizer_args={"lr": 0.1}, optimizer_type="SGD")
+    assert len(sopt.state) == 0                              # type changed: the saved moments are not loaded (:420-423)
 
 
 def test_forgiving_restore_skips_mismatches_and_strips_dataparallel_prefix():

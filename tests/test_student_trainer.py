@@ -73,11 +73,12 @@ def test_surgery_keeps_reference_checkpoint_layout():
 def test_grad_bucket_views_and_confusion_matrix():
     st = make_student()
     bucket = kdcc.GradBucket(st.trainable_parameters())
-    assert bucket.flat.numel() == sum(p.numel() for p in st.trainable_parameters())
+    assert bucket.flat.numel() == sum(-(-p.numel() // 32) * 32 for p in st.trainable_parameters())
+    assert all((p.grad.data_ptr() - bucket.flat.data_ptr()) % 128 == 0 for p in bucket.params)
     for p in bucket.params:
         assert p.grad.data_ptr() >= bucket.flat.data_ptr()
         p.grad.fill_(1.0)
-    assert float(bucket.flat.sum()) == bucket.flat.numel()
+    assert float(bucket.flat.sum()) == sum(p.numel() for p in bucket.params) == bucket.dense().numel()   # padding stays zero
     bucket.zero()
     assert all(float(p.grad.abs().sum()) == 0 for p in bucket.params)
 
@@ -97,7 +98,7 @@ def _ddp_worker(rank, world, port, out):
         ref.load_state_dict(model.state_dict())
         ((ref(x_all) - y_all) ** 2).mean().backward()   # mean over the global batch
         ref_flat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
-        out.put(float((bucket.flat - ref_flat).abs().max()))
+        out.put(float((bucket.dense() - ref_flat).abs().max()))
     dist.barrier()
     dist.destroy_process_group()
 
