@@ -39,17 +39,22 @@ def plan_51m():
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kdcc", choices=["kdcc", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="images (1024^2 crops) per GPU per step")
     ap.add_argument("--crop", type=int, default=1024)
     ap.add_argument("--dw", default="k9d5p20", help="depthwise geometry kKdDpP (Cityscapes cfgs: k9d5p20; CIFAR: k3d1p1)")
-    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"],
-                    help="activation layout: nchw = the reference's (tensor-core depthwise), nhwc = channels_last kernels")
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc", "nhwc_native"],
+                    help="activation layout of the block inputs and outputs: nchw = the reference's; nhwc = channels_last I/O, k > 3 re-laid to channel planes at the block boundary (tensor-core depthwise); nhwc_native = NHWC CUDA-core kernels throughout")
     ap.add_argument("--kd-grad", action="store_true", help="also emit d KD / d logits (ClassificationTrainer path)")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip timing the stock-torch CUDA calls of the same path (the bar)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the modules-API run and the k3d1p1 sub-runs")
+    ap.add_argument("--api-steps", type=int, default=10, help="timed steps of the drop-in modules-API run")
+    ap.add_argument("--whole-steps", type=int, default=6, help="timed steps of the whole-step run with the DeepLabV3+ trunk (0 = skip)")
+    ap.add_argument("--trunk-format", default="channels_last", choices=["nchw", "channels_last"], help="memory format of the harness trunk")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim.RAdam + a separate weight cast instead of the fused kdcc RAdam step")
     ap.add_argument("--graph", action="store_true",
                     help="replay a CUDA graph of the pass instead of stream launches (measured: 475.8 vs 474.5 img/s, i.e. the "
@@ -76,8 +81,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons.  Started BEFORE the warm-up (nvidia-smi needs a moment to produce its first
+    line); `stop(t0, t1)` keeps the samples whose time stamp falls inside the timed region [t0, t1] (datetime.now())."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -88,12 +94,13 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "25"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -102,17 +109,22 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, reasons, smax = [], set(), None
+        sm, power, reasons, smax, total = [], [], set(), None, 0
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
+                if len(f) < 8:
                     continue
+                total += 1
                 try:
-                    sm.append(float(f[0])); smax = float(f[1])
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                    if t0 is not None and not (t0 <= ts <= t1):
+                        continue
+                    sm.append(float(f[1])); smax = float(f[2])
+                    power.append(float(f[3]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             os.unlink(self.path)
@@ -120,7 +132,8 @@ class ClockSampler:
             pass
         if sm:
             sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm),
+                       samples_whole_run=total, power_w_max=max(power) if power else None)
         return out
 
 
@@ -190,6 +203,290 @@ def cpu_reference_image_seconds(plan, maps, geom, budget_s, crop):
     return total, sample
 
 
+def gpu_stock_baseline(plan, batch, maps, geom, crop, dev, iters=3):
+    """The bar: the reference's own calls for this path -- F.conv2d(groups=C)
+    (depthwise_separable_conv.py:12), the 1x1 F.conv2d (:13), F.kl_div over log_softmax / softmax (losses/KLDiv.py:20-22),
+    nn.MSELoss * num_classes (losses/MSELoss.py:16) and their autograd -- on THIS GPU with stock PyTorch
+    (ATen / cuDNN / cuBLAS), in the two forms a user would run them: fp32 NCHW exactly as the reference is written (TF32
+    off, its era's default) and bf16 channels_last.  Each distinct site shape is timed once per form (CUDA events, 1
+    warm-up + `iters` runs) and weighted by its multiplicity in the plan; plus torch.matmul in bf16 on the plan's GEMM
+    shapes.  Returns per-family ms per step, comparable with `kernels[...]["ms_per_step"]`."""
+    import torch
+    import torch.nn.functional as F
+    k, d, p = geom
+    shapes = {}
+    for s_ in plan:
+        shapes[s_] = shapes.get(s_, 0) + 1
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+
+    def timed(fn):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    for form, dtype, fmt in (("fp32_nchw", torch.float32, torch.contiguous_format), ("bf16_channels_last", torch.bfloat16, torch.channels_last)):
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        fam = {"dw_fwd": 0.0, "dw_bwd": 0.0, "pw_fwd": 0.0, "pw_bwd": 0.0, "hint_loss": 0.0}
+        for (ci, co), count in shapes.items():
+            x = torch.randn(batch, ci, maps, maps, device=dev, dtype=dtype).contiguous(memory_format=fmt).requires_grad_(True)
+            w_dw = ((torch.rand(ci, 1, k, k, device=dev) - 0.5).to(dtype)).requires_grad_(True)
+            w_pw = ((torch.rand(co, ci, 1, 1, device=dev) - 0.5).to(dtype)).requires_grad_(True)
+            teacher = torch.randn(batch, co, maps, maps, device=dev, dtype=dtype).contiguous(memory_format=fmt)
+            mid = F.conv2d(x, w_dw, None, 1, p, d, ci)
+            g_mid = torch.randn_like(mid)
+            fam["dw_fwd"] += count * timed(lambda: F.conv2d(x, w_dw, None, 1, p, d, ci))
+            fam["dw_bwd"] += count * timed(lambda: torch.autograd.grad(mid, (x, w_dw), g_mid, retain_graph=True))
+            mid_l = mid.detach().requires_grad_(True)
+            y = F.conv2d(mid_l, w_pw)
+            g_y = torch.randn_like(y)
+            fam["pw_fwd"] += count * timed(lambda: F.conv2d(mid_l, w_pw))
+            fam["pw_bwd"] += count * timed(lambda: torch.autograd.grad(y, (mid_l, w_pw), g_y, retain_graph=True))
+            y_l = y.detach().requires_grad_(True)
+
+            def hint():
+                loss = F.mse_loss(y_l, teacher) * 1000
+                torch.autograd.grad(loss, y_l)
+            fam["hint_loss"] += count * timed(hint)
+            del x, w_dw, w_pw, teacher, mid, g_mid, mid_l, y, g_y, y_l
+        out[form] = {k_: round(v, 4) for k_, v in fam.items()}
+    # KD loss on the logits: fp32 NCHW as written (value only, as the layerwise loop evaluates it under no_grad)
+    ls, lt = 3 * torch.randn(batch, 19, crop, crop, device=dev), 3 * torch.randn(batch, 19, crop, crop, device=dev)
+
+    def kl():
+        with torch.no_grad():
+            return F.kl_div(F.log_softmax(ls / 1.0, dim=1), F.softmax(lt / 1.0, dim=1), reduction="mean") * 19
+    out["fp32_nchw"]["kd_loss"] = round(timed(kl), 4)
+    del ls, lt
+    # cuBLAS bf16 on the plan's GEMMs (forward shape M = pixels, K = C_in, N = C_out)
+    mm = []
+    M = batch * maps * maps
+    for (ci, co), count in shapes.items():
+        a = torch.randn(M, ci, device=dev, dtype=torch.bfloat16)
+        b = torch.randn(ci, co, device=dev, dtype=torch.bfloat16)
+        ms = timed(lambda: torch.matmul(a, b))
+        mm.append({"mkn": [M, ci, co], "count": count, "ms": round(ms, 4), "tflops": round(2.0 * M * ci * co / (ms * 1e-3) / 1e12, 1)})
+        del a, b
+    out["matmul_bf16"] = mm
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.cuda.empty_cache()
+    return out
+
+
+def api_modules_run(plan, batch, maps, geom, crop, dev, world, steps, seed):
+    """The same pass through the DROP-IN API a reference user gets: kdcc.DepthwiseSeparableBlock modules
+    (the class DepthwiseStudent.replace instantiates) + kdcc.MSELoss / kdcc.KLDivergenceLoss + torch autograd +
+    kdcc.GradBucket + kdcc.optim.RAdam, i.e. the loop body of trainer/layerwise_trainer.py:223-239 over the nine sites.
+    Returns img/s (device-timed, max over ranks) and the launch count of one step."""
+    import torch
+    import torch.distributed as dist
+    import kdcc
+    k, d, p = geom
+    torch.manual_seed(seed)
+    blocks = [kdcc.DepthwiseSeparableBlock(ci, co, k, p, d, ci, None).to(dev) for ci, co in plan]
+    params = [prm for b in blocks for prm in b.parameters()]
+    bucket = kdcc.GradBucket(params)
+    opt = kdcc.optim.RAdam(params, lr=5e-3)
+    hint_crit, kd_crit = kdcc.MSELoss(num_classes=1000), kdcc.KLDivergenceLoss(temperature=1)
+    # the first replaced conv's input comes from frozen layers only: no input gradient (SURVEY.md 3.4)
+    xs = [torch.randn(batch, ci, maps, maps, device=dev).to(torch.bfloat16).requires_grad_(i > 0) for i, (ci, _) in enumerate(plan)]
+    ts = [torch.randn(batch, co, maps, maps, device=dev).to(torch.bfloat16) for _, co in plan]
+    ls, lt = 3 * torch.randn(batch, 19, crop, crop, device=dev), 3 * torch.randn(batch, 19, crop, crop, device=dev)
+
+    def one_step():
+        hint = 0
+        for blk, x, t in zip(blocks, xs, ts):
+            hint = hint + hint_crit(blk(x), t)
+        with torch.no_grad():
+            kd = kd_crit(ls, lt)
+        hint.backward()
+        for x in xs:
+            x.grad = None
+        bucket.all_reduce_mean()
+        opt.step()
+        bucket.zero()
+        return hint, kd
+
+    for _ in range(3):
+        one_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        hint, kd = one_step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    res = {"value": world * batch * steps / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms / steps, "steps": steps,
+           "api": "kdcc.DepthwiseSeparableBlock x%d + kdcc.MSELoss + kdcc.KLDivergenceLoss + autograd + kdcc.GradBucket + kdcc.optim.RAdam" % len(plan),
+           "losses": {"hint": float(hint), "kd": float(kd)}}
+    del blocks, params, bucket, opt, xs, ts, ls, lt
+    torch.cuda.empty_cache()
+    return res
+
+
+def whole_step_run(batch, crop, dev, world, steps, trunk_format, seed):
+    """BASELINE.json's metric as named: one layerwise-KD training step at crop x crop with the trunk in the loop --
+    frozen DeepLabV3+/WideResNet38 teacher forward, student forward (the frozen trunk with the nine kdcc cheap-conv blocks
+    of cfg/cityscapes/51M_deeplab_all.json swapped in by kdcc.prepare_train_epoch), hint MSE over the nine hooked pairs,
+    backward (kdcc kernels in the blocks, cuDNN dgrad through the frozen convs between them), gradient all-reduce, fused
+    RAdam, plus what the reference loop evaluates for logging every step (supervised CE of both nets, the logits KD term,
+    both IoU confusion matrices -- the latter on the device instead of the reference's D2H + numpy).
+    The trunk is harness (stock PyTorch bf16, cuDNN); this is the drop-in API end to end: kdcc.DepthwiseStudent +
+    kdcc.LayerwiseStep.  Every step's images and labels are copied from pinned host memory inside the timed region and
+    the step's losses are read back, so this is also the end-to-end number."""
+    import torch
+    import torch.distributed as dist
+    import kdcc
+    from kdcc.trainer import prepare_train_epoch
+    from harness.deeplab_wrn38 import DeepWV3Plus, pruning_section
+    torch.backends.cudnn.benchmark = True
+    fmt = torch.channels_last if trunk_format == "channels_last" else torch.contiguous_format
+    torch.manual_seed(0)                      # the same frozen teacher on every rank
+    teacher = DeepWV3Plus(19).to(dev).to(torch.bfloat16).to(memory_format=fmt)
+    model = kdcc.DepthwiseStudent(teacher, {"trainer": {"verbosity": 2}})
+    del teacher
+    opt = prepare_train_epoch(model, pruning_section(), 1, None, lambda ps: kdcc.optim.RAdam(ps, lr=5e-3))
+    crit = [torch.nn.CrossEntropyLoss(ignore_index=255), kdcc.KLDivergenceLoss(temperature=1), kdcc.MSELoss(num_classes=1000)]
+    step = kdcc.LayerwiseStep(model, crit, opt, accumulation_steps=1)
+    cm_s, cm_t = kdcc.ConfusionMatrix(19, 255, device=dev), kdcc.ConfusionMatrix(19, 255, device=dev)
+    g = torch.Generator().manual_seed(1000 + seed)
+    h_img = torch.randn(batch, 3, crop, crop, generator=g).pin_memory()
+    h_lab = torch.randint(0, 19, (batch, crop, crop), generator=g)
+    h_lab[torch.rand(batch, crop, crop, generator=g) < 0.05] = 255
+    h_lab = h_lab.pin_memory()
+    d_img = [torch.empty(batch, 3, crop, crop, device=dev) for _ in range(2)]
+    d_lab = [torch.empty(batch, crop, crop, dtype=torch.long, device=dev) for _ in range(2)]
+    out_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied, consumed = [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+    h2d = h_img.numel() * 4 + h_lab.numel() * 8
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i & 1])
+            d_img[i & 1].copy_(h_img, non_blocking=True)
+            d_lab[i & 1].copy_(h_lab, non_blocking=True)
+            copied[i & 1].record(copy_stream)
+
+    def run(n):
+        main = torch.cuda.current_stream()
+        for c in consumed:
+            c.record(main)
+        issue_copy(0)
+        for i in range(n):
+            if i + 1 < n:
+                issue_copy(i + 1)
+            main.wait_event(copied[i & 1])
+            data = d_img[i & 1].to(torch.bfloat16).contiguous(memory_format=fmt)
+            out = step(data, d_lab[i & 1], batch_idx=i)
+            with torch.no_grad():
+                cm_s.update(out["output_st"].float(), d_lab[i & 1])
+                cm_t.update(out["output_tc"].float(), d_lab[i & 1])
+            consumed[i & 1].record(main)
+            out_host.copy_(torch.stack([out["hint_loss"].float(), out["kd_loss"].float(), out["supervised_loss"].float(),
+                                        out["teacher_loss"].float()]), non_blocking=True)
+
+    run(3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(steps)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    res = {"value": world * batch * steps / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms / steps, "steps": steps,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16, "trunk": "DeepLabV3+ WideResNet38 (harness/deeplab_wrn38.py), bf16 %s, "
+           "stock PyTorch / cuDNN; 137.10 M teacher, 85.96 M student, 7.84 M trainable" % trunk_format,
+           "api": "kdcc.DepthwiseStudent + kdcc.prepare_train_epoch(cfg 51M_deeplab_all) + kdcc.LayerwiseStep + kdcc.optim.RAdam",
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
+           "last_losses": {"hint": float(out_host[0]), "kd": float(out_host[1]), "supervised": float(out_host[2]), "teacher": float(out_host[3])}}
+    del model, step, opt, d_img, d_lab
+    torch.cuda.empty_cache()
+    return res
+
+
+def workload_config(args, world, n_sites, trainable=None):  # noqa: ARG001 (trainable kept for callers; derived below)
+    """`config` of the JSON line -- the same dict for both arms (the driver compares them)."""
+    maps = args.crop // 8
+    cfg = {"workload": "%s hot path: %d cheap-conv sites (dw %s + pw GEMM) fwd+bwd, hint MSE x%d, KD loss on (N,19,%d,%d), "
+                       "grad all-reduce, RAdam; frozen trunk not run" % (PLAN_NAME, n_sites, args.dw, n_sites, args.crop, args.crop),
+           "global_batch": world * args.batch, "per_gpu_batch": args.batch, "crop": args.crop, "feature_maps": "%dx%d" % (maps, maps),
+           "parallelism": "dp%d" % world, "layout": args.layout}
+    kk = parse_geom(args.dw)[0] ** 2
+    cfg["trainable_params"] = sum(ci * kk + co * ci for ci, co in plan_51m())
+    return cfg
+
+
+_CPU_WHOLE = {}
+
+
+def cpu_whole_step_image_seconds(crop, small=256):
+    """Seconds the reference's torch-CPU path needs for one image of a WHOLE layerwise-KD step (teacher forward, student
+    forward with the nine replaced blocks, hint MSE, backward, RAdam): run at a `small` x `small` crop and scaled by area
+    (BASELINE.md 3.3).  Trunk = harness/deeplab_wrn38.py (bit-identical to the reference class, tests/test_harness_trunk.py),
+    blocks and losses = oracle/torch_port.py (the reference's own torch calls)."""
+    import torch
+    from torch import nn
+    import kdcc
+    from kdcc.trainer import prepare_train_epoch
+    from harness.deeplab_wrn38 import DeepWV3Plus, PRUNING_51M, pruning_section
+    from oracle import torch_port as tp
+    torch.set_num_threads(os.cpu_count() or 1)
+    if "model" not in _CPU_WHOLE:
+        class PortBlock(nn.Module):   # depthwise_separable_conv.py:4-14 through the torch port
+            def __init__(self, blk):
+                super().__init__()
+                self.w_dw, self.w_pw = nn.Parameter(blk.separable_conv.weight.detach().clone()), nn.Parameter(blk.pointwise_conv.weight.detach().clone())
+                self.p, self.d = blk.separable_conv.padding[0], blk.separable_conv.dilation[0]
+
+            def forward(self, x):
+                return tp.block_forward(x, self.w_dw, self.w_pw, self.p, self.d)
+
+        torch.manual_seed(0)
+        model = kdcc.DepthwiseStudent(DeepWV3Plus(19), {"trainer": {"verbosity": 2}})
+        prepare_train_epoch(model, pruning_section(), 1, None, lambda ps: torch.optim.SGD(ps, lr=0.0))
+        for n in PRUNING_51M["names"]:
+            model._set_block(n, PortBlock(model.get_block(n, model.student)), model.student)
+        model.register_hint_layers(PRUNING_51M["names"])
+        _CPU_WHOLE["model"] = model
+        _CPU_WHOLE["opt"] = torch.optim.RAdam(model.trainable_parameters(), lr=5e-3)
+    model, opt = _CPU_WHOLE["model"], _CPU_WHOLE["opt"]
+    x = torch.randn(1, 3, small, small)
+    t0 = time.perf_counter()
+    out_st, out_tc = model(x)
+    hint = sum(tp.mse_loss(a, b, 1000) for a, b in zip(model.student_hidden_outputs, model.teacher_hidden_outputs))
+    with torch.no_grad():
+        tp.kl_div_loss(out_st, out_tc, 1.0)
+    hint.backward()
+    opt.step()
+    opt.zero_grad()
+    sec = time.perf_counter() - t0
+    return sec * (crop / float(small)) ** 2, "1 image at %dx%d scaled x%g by area; torch CPU fp32 NCHW, DeepLabV3+ WRN38 teacher + student" % (small, small, (crop / float(small)) ** 2)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -204,14 +501,24 @@ def run_reference(args, rank):
     sec = sum(times) / len(times)
     cores = os.cpu_count() or 1
     val = 1.0 / sec
+    # the whole training step (trunk in the loop) on the CPU, beside our arm's `whole_step`
+    whole = None
+    if geom == (9, 5, 20) and not args.no_extras:
+        try:
+            cpu_whole_step_image_seconds(args.crop)                       # builds the model, warms the thread pool
+            ws = [cpu_whole_step_image_seconds(args.crop) for _ in range(2)]
+            whole = {"value": 1.0 / (sum(w[0] for w in ws) / len(ws)), "unit": "img/s", "cores": cores, "sample": ws[0][1]}
+        except Exception as exc:
+            whole = {"error": repr(exc)[:200]}
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": PLAN_NAME + " hot path, 1024x1024 crop, dw " + args.dw, "global_batch": 1,
-                       "note": "reference = its own torch calls on the host CPU (oracle/torch_port.py); one image per step"},
+            "warmup": args.warmup, "ms_per_step": args.batch * sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, max(1, args.gpus), len(plan_51m())),
+            "note": "reference = its own torch calls on the host CPU (oracle/torch_port.py).  Every image of a batch costs the same, so a "
+                    "step times ONE image -- each distinct site shape once, weighted by its multiplicity in the plan -- and the img/s "
+                    "is that per-image time extrapolated; ms_per_step is the extrapolated time of a batch of %d" % args.batch,
             "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "whole_step": whole, "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -236,8 +543,12 @@ def run_kdcc(args, rank, world, local_rank):
     plan = plan_51m()
     N = args.batch
     logits_shape = (N, 19, args.crop, args.crop)
+    # the first replaced conv is fed by frozen layers only, so its input gradient is never needed;
+    # every later site's dX continues into the (frozen-weight) student graph towards the earlier trainable blocks
+    need_dx = [False] + [True] * (len(plan) - 1)
     hp = HotPathStep(plan, N, maps, maps, k, d, p, dtype=torch.bfloat16, device=dev, logits_shape=logits_shape,
-                     kd_temperature=1.0, hint_num_classes=1000.0, accumulation_steps=1, kd_grad=args.kd_grad, seed=rank, layout=args.layout)
+                     kd_temperature=1.0, hint_num_classes=1000.0, accumulation_steps=1, kd_grad=args.kd_grad, need_dx=need_dx,
+                     seed=rank, layout=args.layout)
     xs, ts, ls, lt = hp.make_inputs(seed=100 + rank)
     param = torch.nn.Parameter(hp.flat_params)
     param.grad = hp.flat_grads
@@ -281,21 +592,24 @@ def run_kdcc(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    import datetime
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # before the warm-up: nvidia-smi takes a moment to deliver its first line
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     log = EventLog()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = datetime.datetime.now()
     e0.record()
     for _ in range(args.steps):
         hint, kd = one_step(log)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = datetime.datetime.now()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     elapsed_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
@@ -303,6 +617,21 @@ def run_kdcc(args, rank, world, local_rank):
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = world * N * args.steps / (elapsed_ms * 1e-3)
+    # N > 1: where the step time goes per rank.  A rank's own kernels (everything but the collective) against the time it
+    # sits in the all-reduce: under the power cap every GPU runs at its own clock, the collective makes all of them wait
+    # for the slowest, so `compute_ms` max - min is the part of the scaling loss no overlap can recover.
+    scaling_diag = None
+    if world > 1:
+        mine = log.durations_ms()
+        comp = sum(sum(v) for n_, v in mine.items() if n_ != "grad_allreduce") / args.steps
+        wait = sum(mine.get("grad_allreduce", [0.0])) / args.steps
+        t = torch.tensor([comp, wait], device=dev)
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        scaling_diag = {"compute_ms_per_rank": [round(float(a[0]), 3) for a in allv],
+                        "allreduce_interval_ms_per_rank": [round(float(a[1]), 3) for a in allv],
+                        "note": "compute = the rank's own kernels per step (CUDA events); allreduce interval = launch + transfer + waiting "
+                                "for the slowest rank.  max(compute) bounds the step from below whatever the collective does"}
 
     # ---- end to end through the public call: pinned host inputs -> device, step, loss back to the host ----
     e2e = None
@@ -359,6 +688,29 @@ def run_kdcc(args, rank, world, local_rank):
                "d2h_bytes_per_step": 8, "steps": args.e2e_steps,
                "pipeline": "H2D of step i+1 on a copy stream overlaps the kernels of step i (two device input sets)", "last_losses": [float(out_host[0]), float(out_host[1])]}
 
+    # ---- the same pass through the drop-in module API (every rank: it contains the gradient all-reduce) ----
+    api = None
+    if not args.no_extras and args.api_steps > 0 and args.layout == "nchw":
+        xs = ts = ls = lt = None
+        if args.e2e_steps > 0:
+            del sets, hx, ht, hls, hlt
+        torch.cuda.empty_cache()
+        api = api_modules_run(plan, N, maps, (k, d, p), args.crop, dev, world, args.api_steps, seed=rank)
+        api["vs_hotpath"] = round(api["value"] / value, 4)
+
+    # ---- BASELINE's metric as named: the whole training step with the frozen trunk in the loop (every rank) ----
+    whole = None
+    if not args.no_extras and args.whole_steps > 0 and (k, d, p) == (9, 5, 20):
+        del hp.mid, hp.dmid, hp.dx, hp.y, hp.dy, hp.ws
+        torch.cuda.empty_cache()
+        try:
+            whole = whole_step_run(N, args.crop, dev, world, args.whole_steps, args.trunk_format, seed=rank)
+            whole["hot_path_share"] = round(ms_per_step / whole["ms_per_step"], 4)
+        except Exception as exc:
+            if world > 1:
+                raise
+            whole = {"error": repr(exc)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -383,8 +735,10 @@ def run_kdcc(args, rank, world, local_rank):
                 entry.update(bound="hbm", achieved=round(work / (per_step_ms * 1e-3) / 1e9, 1), unit="GB/s",
                              frac=round(work / (per_step_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4))
             else:
+                # the timed region is a fraction of a second at the boost clock: the burst cuBLAS figure is the honest peak
                 entry.update(bound="tensor", achieved=round(work / (per_step_ms * 1e-3) / 1e12, 1), unit="TFLOP/s",
-                             frac=round(work / (per_step_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], 4))
+                             frac=round(work / (per_step_ms * 1e-3) / 1e12 / pk["bf16_tflops"], 4),
+                             frac_of_sustained=round(work / (per_step_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], 4))
             if per_step_ms > dom_ms:
                 dominant, dom_ms = name, per_step_ms
         kernels[name] = entry
@@ -394,7 +748,8 @@ def run_kdcc(args, rank, world, local_rank):
     traffic = None
     try:
         if (N, args.dw, args.layout, args.crop) == (4, "k9d5p20", "nchw", 1024):
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            import glob
+            with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]) as f:
                 traffic = json.load(f)["families"][dominant]["dram_bytes_per_step"]
     except Exception:
         traffic = None
@@ -405,9 +760,9 @@ def run_kdcc(args, rank, world, local_rank):
                 "bound by the issue cost of their small-N MMAs (90 x 59 clk conv, 72 x 74 clk dW per plane, DESIGN.md 4.0/4.1), "
                 "not by HBM; frac is still reported against the HBM copy peak" % dk["launches_per_step"])
     roofline = {"kernel": dominant, "bound": dk["bound"], "achieved": dk["achieved"],
-                "peak": pk["hbm_gbs"] if dk["bound"] == "hbm" else pk["bf16_tflops_sustained"], "unit": dk["unit"],
+                "peak": pk["hbm_gbs"] if dk["bound"] == "hbm" else pk["bf16_tflops"], "unit": dk["unit"],
                 "frac": dk["frac"], "traffic": traffic, "algorithmic_bytes": alg[dominant][0] if alg[dominant][1] == "B" else None,
-                "peak_source": pk["source"] + (" copy bandwidth" if dk["bound"] == "hbm" else " sustained cuBLAS bf16"),
+                "peak_source": pk["source"] + (" copy bandwidth" if dk["bound"] == "hbm" else " burst cuBLAS bf16"),
                 "note": note}
     try:  # the resource that actually binds the dominant family (an annotation: it must never break the line)
         if dominant == "dw_bwd" and k >= 7:
@@ -421,19 +776,71 @@ def run_kdcc(args, rank, world, local_rank):
         sec, sample = cpu_reference_image_seconds(plan, maps, (k, d, p), 25.0, args.crop)
         cpu_baseline = {"value": 1.0 / sec, "unit": "img/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
 
+    # ---- the bar: stock-torch CUDA on the same shapes, and per-site GEMM rates against cuBLAS ----
+    gpu_baseline = None
+    if not args.no_gpu_baseline and world == 1:
+        try:
+            torch.cuda.empty_cache()
+            gb = gpu_stock_baseline(plan, N, maps, (k, d, p), args.crop, dev)
+            ours = {n_: kernels[n_]["ms_per_step"] for n_ in kernels}
+            ours["pw_bwd"] = ours.get("pw_bwd_dx", 0) + ours.get("pw_bwd_dw", 0)
+            table = {}
+            for fam in ("dw_fwd", "dw_bwd", "pw_fwd", "pw_bwd", "hint_loss", "kd_loss"):
+                stock = {form: gb[form][fam] for form in ("fp32_nchw", "bf16_channels_last") if fam in gb[form]}
+                best = min(stock.values())
+                table[fam] = {"kdcc_ms": round(ours[fam], 4), "stock_ms": stock, "speedup_vs_best_stock": round(best / ours[fam], 2)}
+            # per-site forward GEMM rate (CUDA events of the timed region, averaged per site) against torch.matmul
+            site_ms = {}
+            per_call = durs.get("pw_fwd", [])
+            for i, site in enumerate(plan):
+                vals = per_call[i::len(plan)]
+                site_ms.setdefault(site, []).extend(vals)
+            for row in gb["matmul_bf16"]:
+                site = (row["mkn"][1], row["mkn"][2])
+                if site in site_ms and site_ms[site]:
+                    ms_ = sum(site_ms[site]) / len(site_ms[site])
+                    row["kdcc_pw_fwd_ms"] = round(ms_, 4)
+                    row["kdcc_pw_fwd_tflops"] = round(2.0 * row["mkn"][0] * row["mkn"][1] * row["mkn"][2] / (ms_ * 1e-3) / 1e12, 1)
+            gpu_baseline = {"what": "the reference's own torch calls for this path on this GPU (ATen / cuDNN / cuBLAS, TF32 off), ms per step "
+                                    "summed over the %d sites: fp32 NCHW as written and bf16 channels_last; pw_bwd = dX + dW; dw_bwd includes dX for every site" % len(plan),
+                            "families": table, "matmul_bf16": gb["matmul_bf16"]}
+        except Exception as exc:  # an annotation: never break the line
+            gpu_baseline = {"error": repr(exc)[:200]}
+
+    kernels_k3 = None
+    if not args.no_extras and world == 1 and (k, d, p) != (3, 1, 1):
+        try:
+            kernels_k3 = {}
+            for lay in ("nchw", "nhwc"):
+                torch.cuda.empty_cache()
+                h3 = HotPathStep(plan, N, maps, maps, 3, 1, 1, dtype=torch.bfloat16, device=dev, logits_shape=None, need_dx=need_dx, seed=7, layout=lay)
+                x3, t3, _, _ = h3.make_inputs(seed=11)
+                for _ in range(3):
+                    h3.step(x3, t3)
+                lg = EventLog()
+                torch.cuda.synchronize()
+                for _ in range(5):
+                    h3.step(x3, t3, log=lg)
+                torch.cuda.synchronize()
+                d3, a3 = lg.durations_ms(), h3.algorithmic()
+                kernels_k3[lay] = {n_: {"ms_per_step": round(sum(d3[n_]) / 5, 4), "achieved": round(a3[n_][0] / (sum(d3[n_]) / 5 * 1e-3) / 1e9, 1),
+                                        "unit": "GB/s", "frac": round(a3[n_][0] / (sum(d3[n_]) / 5 * 1e-3) / 1e9 / pk["hbm_gbs"], 4)}
+                                   for n_ in ("dw_fwd", "dw_bwd")}
+                del h3, x3, t3
+            kernels_k3["note"] = "the same nine sites with the CIFAR / north-star 3x3 geometry (k3 d1 p1), 5 timed steps per layout"
+        except Exception as exc:
+            kernels_k3 = {"error": repr(exc)[:200]}
+
     line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "%s hot path: %d cheap-conv sites (dw %s + pw GEMM) fwd+bwd, hint MSE x%d, KD loss on (N,19,%d,%d), "
-                                   "grad all-reduce, RAdam; frozen trunk not run" % (PLAN_NAME, len(plan), args.dw, len(plan), args.crop, args.crop),
-                       "global_batch": world * N, "per_gpu_batch": N, "crop": args.crop, "feature_maps": "%dx%d" % (maps, maps),
-                       "parallelism": "dp%d" % world, "trainable_params": hp.num_trainable, "layout": args.layout,
-                       "launch": ("CUDA graph of the pass replayed per step; per-kernel times = CUDA events inside the graph, last timed step"
-                                  if use_graph else "stream launches; per-kernel times = CUDA events between launches, all timed steps"),
-                       "cache": "inputs larger than L2 (per-step working set of several GB >> 126 MB), no explicit flush"},
+            "config": dict(workload_config(args, world, len(plan), hp.num_trainable),
+                           launch=("CUDA graph of the pass replayed per step; per-kernel times = CUDA events inside the graph, last timed step"
+                                   if use_graph else "stream launches; per-kernel times = CUDA events between launches, all timed steps"),
+                           cache="inputs larger than L2 (per-step working set of several GB >> 126 MB), no explicit flush"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": (hp.launches_per_step + (0 if args.torch_optimizer else 1)) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
-            "losses": {"hint": float(hint), "kd": float(kd)}}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline, "api_modules": api, "whole_step": whole, "scaling_diag": scaling_diag,
+            "kernels": kernels, "kernels_k3": kernels_k3, "losses": {"hint": float(hint), "kd": float(kd)}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -142,6 +142,14 @@ int kdcc_hint_loss(const void *s, const void *t, const float *w, int w_per_sampl
 int kdcc_cast_f32_to_bf16(const float *src, void *dst, long n, kdcc_stream_t stream);
 /* buf[i] *= *dev_scalar   (applies autograd's upstream 0-dim grad to an emitted gradient) */
 int kdcc_scale_inplace(void *buf, const float *dev_scalar, long n, int dtype, kdcc_stream_t stream);
+/* buf[i] *= *dev_scalar / expected: the loss kernels fold the upstream value a caller EXPECTS (grad_scale) into the
+ * gradient they emit; backward then only verifies it -- when *dev_scalar == expected the launch touches no memory, otherwise
+ * it rescales, so the result is right either way without a host read of the device scalar. */
+int kdcc_scale_inplace_expect(void *buf, const float *dev_scalar, float expected, long n, int dtype, kdcc_stream_t stream);
+/* Activation layout conversion at a block boundary (layout_convert.cu): dst = src re-laid from NHWC to NCHW (to_nchw = 1) or
+ * back (to_nchw = 0); bf16, C % 8 == 0, HW % 8 == 0.  Lets a channels_last trunk feed the NCHW tensor-core depthwise kernels
+ * of models/students/transform_blocks/depthwise_separable_conv.py:11-14's replacement. */
+int kdcc_layout_convert(const void *src, void *dst, int N, int C, long HW, int to_nchw, int dtype, kdcc_stream_t stream);
 /* out[j] = sum_m a[m][j]  (bias gradients), a [M,Nc] in dtype, out fp32 */
 int kdcc_colsum(const void *a, float *out, void *workspace, size_t workspace_bytes, long M, int Nc,
                 int dtype, kdcc_stream_t stream);

@@ -34,6 +34,8 @@ SIGNATURES = {
     "kdcc_hint_loss": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _i, _l, _i, _f, _i, _f, _vp]),
     "kdcc_cast_f32_to_bf16": (_i, [_vp, _vp, _l, _vp]),
     "kdcc_scale_inplace": (_i, [_vp, _vp, _l, _i, _vp]),
+    "kdcc_scale_inplace_expect": (_i, [_vp, _vp, _f, _l, _i, _vp]),
+    "kdcc_layout_convert": (_i, [_vp, _vp, _i, _i, _l, _i, _i, _vp]),
     "kdcc_colsum": (_i, [_vp, _vp, _vp, _sz, _l, _i, _i, _vp]),
     "kdcc_colsum_workspace_bytes": (_sz, [_l, _i]),
     "kdcc_confusion_update": (_i, [_vp, _vp, _vp, _i, _i, _l, _l, _l, _i, _i, _vp]),

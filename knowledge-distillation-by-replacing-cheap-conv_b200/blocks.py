@@ -30,8 +30,10 @@ class DepthwiseSeparableBlock(nn.Module):
 
     def forward(self, x):
         dw, pw = self.separable_conv, self.pointwise_conv
+        # a channels_last caller gets a channels_last result whatever layout the kernels ran in between
+        cl = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
         x = F_kdcc.depthwise_conv(x, dw.weight, dw.bias, self._k, self._d, self._p)
-        x = F_kdcc.pointwise_conv(x, pw.weight, pw.bias)
+        x = F_kdcc.pointwise_conv(x, pw.weight, pw.bias, out_channels_last=cl)
         return x
 
     @torch.no_grad()
@@ -48,5 +50,6 @@ class DepthwiseSeparableBlock(nn.Module):
         shift = beta - bn.running_mean.float() * scale
         if pw.bias is not None:
             shift = shift + pw.bias.float() * scale
+        cl = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
         x = F_kdcc.depthwise_conv(x, dw.weight, dw.bias, self._k, self._d, self._p)
-        return F_kdcc.pointwise_conv(x, pw.weight, None, scale, shift.contiguous(), relu)
+        return F_kdcc.pointwise_conv(x, pw.weight, None, scale, shift.contiguous(), relu, out_channels_last=cl)

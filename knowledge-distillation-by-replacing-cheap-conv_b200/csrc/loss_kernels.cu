@@ -461,9 +461,21 @@ __global__ void cast_f32_to_bf16_kernel(const float *__restrict__ src, __nv_bflo
 }
 
 template <typename T>
-__global__ void scale_inplace_kernel(T *__restrict__ buf, const float *__restrict__ scalar, long n) {
-  const float g = __ldg(scalar);
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+__global__ void scale_inplace_kernel(T *__restrict__ buf, const float *__restrict__ scalar, float expected, long n) {
+  // buf *= scalar / expected.  The forward pass already folded `expected` into the emitted gradient; when autograd's
+  // upstream value is what was expected (the usual case) every thread leaves without touching memory.
+  const float g = __ldg(scalar) / expected;
+  if (g == 1.f) return;
+  constexpr int V = 16 / sizeof(T);
+  const long nv = (reinterpret_cast<uintptr_t>(buf) & 15) == 0 ? n / V : 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) {
+    uint4 u = reinterpret_cast<uint4 *>(buf)[i];
+    T *e = reinterpret_cast<T *>(&u);
+#pragma unroll
+    for (int j = 0; j < V; ++j) e[j] = from_f32<T>(to_f32(e[j]) * g);
+    reinterpret_cast<uint4 *>(buf)[i] = u;
+  }
+  for (long i = nv * V + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     buf[i] = from_f32<T>(to_f32(buf[i]) * g);
 }
 
@@ -683,16 +695,20 @@ KDCC_API int kdcc_cast_f32_to_bf16(const float *src, void *dst, long n, kdcc_str
   return launch_status();
 }
 
-KDCC_API int kdcc_scale_inplace(void *buf, const float *dev_scalar, long n, int dtype, kdcc_stream_t stream) {
-  if (!buf || !dev_scalar || n < 0) return KDCC_EINVAL;
+KDCC_API int kdcc_scale_inplace_expect(void *buf, const float *dev_scalar, float expected, long n, int dtype, kdcc_stream_t stream) {
+  if (!buf || !dev_scalar || n < 0 || !(expected != 0.f)) return KDCC_EINVAL;
   if (n == 0) return KDCC_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = (int)min((long)kNumSMs * 8, ceil_div<long>(n, 256));
-  if (dtype == KDCC_F32) scale_inplace_kernel<float><<<grid, 256, 0, st>>>(static_cast<float *>(buf), dev_scalar, n);
+  const int grid = (int)min((long)kNumSMs * 8, ceil_div<long>(n, 256 * 8));
+  if (dtype == KDCC_F32) scale_inplace_kernel<float><<<grid, 256, 0, st>>>(static_cast<float *>(buf), dev_scalar, expected, n);
   else if (dtype == KDCC_BF16)
-    scale_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<__nv_bfloat16 *>(buf), dev_scalar, n);
+    scale_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<__nv_bfloat16 *>(buf), dev_scalar, expected, n);
   else return KDCC_EINVAL;
   return launch_status();
+}
+
+KDCC_API int kdcc_scale_inplace(void *buf, const float *dev_scalar, long n, int dtype, kdcc_stream_t stream) {
+  return kdcc_scale_inplace_expect(buf, dev_scalar, 1.f, n, dtype, stream);
 }
 
 static int colsum_splits(long M) { return (int)max(1L, min(256L, M / 256)); }

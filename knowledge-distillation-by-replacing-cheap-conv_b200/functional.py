@@ -10,6 +10,8 @@ Reference call sites replaced (reference file:line):
   kd_loss             losses/KLDiv.py:19-23, losses/EnsembleKLDiv.py:18-22
   hint_loss           losses/WeightedHintMSELoss.py:12-16, losses/MSELoss.py:14-16
 """
+import os
+
 import torch
 
 from . import _abi
@@ -57,8 +59,31 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+_WS = {}
+
+
 def _workspace(nbytes, device):
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    """Scratch for one kernel call.  One buffer per (device, stream), grown on demand and reused: launches on a stream
+    are serialised, so the next call may overwrite what the previous one has finished with -- and the caching allocator
+    is not asked twice per block and step."""
+    nbytes = max(int(nbytes), 16)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _WS[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return buf
+
+
+_DISPATCH = {}
+
+
+def _supported(op, N, H, W, C, Cout, k, dil, pad, layout, code):
+    """kdcc_dispatch_name(...) != "unsupported", memoised (it is asked for every forward of every block)."""
+    key = (op, N, H, W, C, Cout, k, dil, pad, layout, code)
+    r = _DISPATCH.get(key)
+    if r is None:
+        r = _DISPATCH[key] = _abi.dispatch_name(*key) != "unsupported"
+    return r
 
 
 def _nhwc(t):
@@ -75,8 +100,35 @@ def _is_plain_nchw(t):
     return t.dim() == 4 and t.is_contiguous() and not t.is_contiguous(memory_format=torch.channels_last)
 
 
+def _is_channels_last(t):
+    """True for a dense channels_last tensor that is not also plain NCHW."""
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def _convertible(t):
+    """kdcc_layout_convert takes bf16 with 16-byte rows in both layouts."""
+    return t.dtype == torch.bfloat16 and t.dim() == 4 and t.shape[1] % 8 == 0 and (t.shape[2] * t.shape[3]) % 8 == 0
+
+
+def _convert(t, to_nchw):
+    """NHWC-physical -> NCHW-physical (or back) through kdcc_layout_convert; `t` must be dense in the source layout."""
+    N, C, H, W = t.shape
+    out = torch.empty((N, C, H, W), dtype=t.dtype, device=t.device,
+                      memory_format=torch.contiguous_format if to_nchw else torch.channels_last)
+    _abi.check(_abi.lib().kdcc_layout_convert(_ptr(t), _ptr(out), N, C, H * W, int(to_nchw), _dtype_code(t), _stream()),
+               "kdcc_layout_convert")
+    return out
+
+
 def _format(t, layout):
-    return t.contiguous() if layout == _abi.NCHW else _nhwc(t)
+    """`t` dense in `layout`; the bf16 re-layout runs in libkdcc (a tiled transpose at HBM speed), anything else in torch."""
+    if layout == _abi.NCHW:
+        if t.is_contiguous():
+            return t
+        return _convert(t, True) if (_is_channels_last(t) and _convertible(t)) else t.contiguous()
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    return _convert(t, False) if (_is_plain_nchw(t) and _convertible(t)) else _nhwc(t)
 
 
 def _empty_like_layout(n, c, h, w, like, layout):
@@ -88,12 +140,57 @@ def _empty_like_layout(n, c, h, w, like, layout):
 @_device_guard
 def cast_weight(w_f32, dtype):
     """fp32 master parameter -> activation dtype through kdcc_cast_f32_to_bf16 (no torch arithmetic)."""
-    if dtype == torch.float32:
+    if w_f32.dtype == dtype:
         return w_f32.contiguous()
+    if w_f32.dtype != torch.float32 or dtype != torch.bfloat16:
+        raise _abi.KdccError("kdcc keeps fp32 master weights and casts them to bf16 activations; got %s -> %s" % (w_f32.dtype, dtype))
     out = torch.empty(w_f32.shape, dtype=torch.bfloat16, device=w_f32.device)
     src = w_f32.contiguous()
     _abi.check(_abi.lib().kdcc_cast_f32_to_bf16(_ptr(src), _ptr(out), src.numel(), _stream()), "kdcc_cast_f32_to_bf16")
     return out
+
+
+# bf16 copies of fp32 master weights, keyed by the parameter object: (parameter version, copy).  A forward reuses the copy
+# while the parameter's version counter has not moved; kdcc.optim.RAdam rewrites the copy inside its fused step and
+# re-stamps it (lp_refreshed), so a training loop never launches a cast after the first step.
+import weakref
+
+_LP = {}   # id(param) -> (weakref to param, version, copy); the weakref's callback drops the entry with the parameter
+
+
+def _lp_entry(param):
+    hit = _LP.get(id(param))
+    return hit if hit is not None and hit[0]() is param else None
+
+
+def _lp_store(param, lp):
+    key = id(param)
+    _LP[key] = (weakref.ref(param, lambda _r, key=key: _LP.pop(key, None)), param._version, lp)
+
+
+def lp_weight(param, dtype):
+    """The activation-dtype copy of `param` (an fp32 master weight), cached across calls."""
+    if param.dtype == dtype:
+        return param.detach()
+    hit = _lp_entry(param)
+    if hit is not None and hit[1] == param._version and hit[2].dtype == dtype and hit[2].device == param.device:
+        return hit[2]
+    lp = cast_weight(param.detach(), dtype)
+    _lp_store(param, lp)
+    return lp
+
+
+def lp_copy_of(param):
+    """The cached low-precision copy of `param`, or None (used by the fused optimizer step to refresh it in place)."""
+    hit = _lp_entry(param)
+    return hit[2] if hit is not None and hit[2].device == param.device else None
+
+
+def lp_refreshed(param):
+    """The optimizer has just rewritten param and its cached copy together: the copy is current for the new version."""
+    hit = _lp_entry(param)
+    if hit is not None:
+        _lp_store(param, hit[2])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -109,9 +206,14 @@ class _DepthwiseConv(torch.autograd.Function):
         code = _dtype_code(x)
         # the reference's own NCHW layout runs on the tensor-core kernels (bf16); channels_last and fp32 run NHWC
         layout = _abi.NHWC
-        if _is_plain_nchw(x) and bias is None and \
-                _abi.dispatch_name(0, N, H, W, C, C, k, dil, pad, _abi.NCHW, code) != "unsupported":
-            layout = _abi.NCHW
+        in_cl = False
+        if bias is None and _supported(0, N, H, W, C, C, k, dil, pad, _abi.NCHW, code):
+            if _is_plain_nchw(x):
+                layout = _abi.NCHW
+            elif k > 3 and _is_channels_last(x) and _convertible(x) and not os.environ.get("KDCC_DW_KEEP_NHWC"):
+                # a channels_last trunk: the large dilated kernels only reach tensor-core speed on channel planes, so the
+                # input is re-laid at the block boundary (layout_convert.cu); 3x3 stays on the streaming NHWC kernels
+                layout, in_cl = _abi.NCHW, True
         x = _format(x, layout)
         w = weight.detach().reshape(C, k * k).float().contiguous()
         b = bias.detach().float().contiguous() if bias is not None else None
@@ -120,6 +222,7 @@ class _DepthwiseConv(torch.autograd.Function):
                                           code, _stream()), "kdcc_dw_fwd")
         ctx.save_for_backward(x, w)
         ctx.geom = (k, dil, pad, bias is not None, weight.shape, layout)
+        ctx.in_cl = in_cl
         return y
 
     @staticmethod
@@ -138,6 +241,8 @@ class _DepthwiseConv(torch.autograd.Function):
         ws = _workspace(L.kdcc_dw_bwd_workspace_bytes(N, H, W, C, k, dil, pad, layout, code), x.device)
         _abi.check(L.kdcc_dw_bwd(_ptr(x), _ptr(w), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws), ws.numel(),
                                  N, H, W, C, k, dil, pad, layout, code, _stream()), "kdcc_dw_bwd")
+        if need_dx and ctx.in_cl:
+            dx = _convert(dx, False)   # the gradient goes back in the layout the input came in
         return dx, (dw.reshape(wshape) if need_dw else None), db, None, None, None
 
 
@@ -152,17 +257,17 @@ def depthwise_conv(x, weight, bias, kernel_size, dilation, padding):
 class _PointwiseConv(torch.autograd.Function):
     @staticmethod
     @_device_guard
-    def forward(ctx, x, weight, bias, scale, shift, relu, residual=None):
+    def forward(ctx, x, weight, bias, scale, shift, relu, residual=None, out_channels_last=False):
         _require_cuda(x, weight, bias)
         N, K, H, W = x.shape
         Co = weight.shape[0]
         M = N * H * W
         code = _dtype_code(x)
         layout = _abi.NHWC
-        if _is_plain_nchw(x) and _abi.dispatch_name(2, N, H, W, K, Co, 1, 1, 0, _abi.NCHW, code) != "unsupported":
+        if _is_plain_nchw(x) and _supported(2, N, H, W, K, Co, 1, 1, 0, _abi.NCHW, code):
             layout = _abi.NCHW
         x = _format(x, layout)
-        w = cast_weight(weight.detach().reshape(Co, K), x.dtype)
+        w = lp_weight(weight, x.dtype).reshape(Co, K)
         y = _empty_like_layout(N, Co, H, W, x, layout)
         fused = scale is not None or shift is not None or relu
         eff_shift = shift
@@ -181,6 +286,8 @@ class _PointwiseConv(torch.autograd.Function):
             _abi.check(_abi.lib().kdcc_pw_fwd(_ptr(x), _ptr(w), _ptr(scale), _ptr(eff_shift), int(bool(relu)),
                                               None if use_act else _ptr(y), _ptr(y) if use_act else None,
                                               M, K, Co, N, layout, code, _stream()), "kdcc_pw_fwd")
+        if out_channels_last and layout == _abi.NCHW and _convertible(y):
+            y = _convert(y, False)          # hand the result back in the caller's (channels_last) layout
         if fused:
             ctx.mark_non_differentiable(y)  # inference-only epilogue (eval-mode BN fold)
         ctx.save_for_backward(x, w)
@@ -217,14 +324,14 @@ class _PointwiseConv(torch.autograd.Function):
             _abi.check(L.kdcc_colsum(_ptr(dyr), _ptr(db), _ptr(ws), ws.numel(), M, Co, code, st), "kdcc_colsum")
         # y = conv + residual: the shortcut receives the output gradient as it is
         dres = dy if (ctx.has_residual and ctx.needs_input_grad[6]) else None
-        return dx, dw, db, None, None, None, dres
+        return dx, dw, db, None, None, None, dres, None
 
 
-def pointwise_conv(x, weight, bias=None, scale=None, shift=None, relu=False, residual=None):
+def pointwise_conv(x, weight, bias=None, scale=None, shift=None, relu=False, residual=None, out_channels_last=False):
     """F.conv2d(x, weight (Co,C,1,1), bias) on libkdcc; optional fused eval-mode BN (scale, shift) + ReLU, optional
     shortcut added in the epilogue (`out = convs(x); out.add_(shortcut)` of a residual block in one kernel;
     differentiable when no BN / ReLU is fused)."""
-    return _PointwiseConv.apply(x, weight, bias, scale, shift, bool(relu), residual)
+    return _PointwiseConv.apply(x, weight, bias, scale, shift, bool(relu), residual, bool(out_channels_last))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -259,7 +366,7 @@ def _logit_strides(t):
 class _KdLoss(torch.autograd.Function):
     @staticmethod
     @_device_guard
-    def forward(ctx, s, t, temperature, target_is_prob):
+    def forward(ctx, s, t, temperature, target_is_prob, expected=1.0):
         _require_cuda(s, t)
         if s.shape != t.shape or s.dim() < 2:
             raise _abi.KdccError("kd loss expects matching (N, C, ...) tensors, got %s and %s" % (tuple(s.shape), tuple(t.shape)))
@@ -278,9 +385,10 @@ class _KdLoss(torch.autograd.Function):
         L = _abi.lib()
         ws = _workspace(L.kdcc_loss_workspace_bytes(), s.device)
         _abi.check(L.kdcc_kd_loss(_ptr(s), _ptr(t), _ptr(ds), _ptr(loss), _ptr(ws), ws.numel(), N, C, HW, bs, cs, ps,
-                                  float(temperature), int(bool(target_is_prob)), _dtype_code(s), 1.0, _stream()),
+                                  float(temperature), int(bool(target_is_prob)), _dtype_code(s), float(expected), _stream()),
                    "kdcc_kd_loss")
         ctx.ds = ds
+        ctx.expected = float(expected)
         return loss
 
     @staticmethod
@@ -288,22 +396,26 @@ class _KdLoss(torch.autograd.Function):
     def backward(ctx, g):
         ds = _take_grad(ctx)
         if ds is None:
-            return None, None, None, None
+            return None, None, None, None, None
         g = g.detach().float().contiguous()
-        _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
-                   "kdcc_scale_inplace")
-        return ds, None, None, None
+        _abi.check(_abi.lib().kdcc_scale_inplace_expect(_ptr(ds), _ptr(g), ctx.expected, ds.numel(), _dtype_code(ds), _stream()),
+                   "kdcc_scale_inplace_expect")
+        return ds, None, None, None, None
 
 
-def kd_loss(inputs, targets, temperature=1.0, target_is_prob=False):
-    """T^2/(N*HW) * sum_pix KL(p_t || softmax(inputs/T)); fp32 0-dim tensor with grad_fn."""
-    return _KdLoss.apply(inputs, targets, float(temperature), bool(target_is_prob))
+def kd_loss(inputs, targets, temperature=1.0, target_is_prob=False, expected_upstream=1.0):
+    """T^2/(N*HW) * sum_pix KL(p_t || softmax(inputs/T)); fp32 0-dim tensor with grad_fn.
+    `expected_upstream`: the value autograd is expected to hand to this node's backward (1 for `loss.backward()`,
+    1/accumulation_steps for `(sum of losses / accumulation_steps).backward()`).  It is folded into the gradient the
+    forward kernel emits; backward verifies it on the device and rescales only if it differs, so it is a performance
+    hint, never a correctness assumption."""
+    return _KdLoss.apply(inputs, targets, float(temperature), bool(target_is_prob), float(expected_upstream))
 
 
 class _KdLossMulti(torch.autograd.Function):
     @staticmethod
     @_device_guard
-    def forward(ctx, s, temperature, weights, *teachers):
+    def forward(ctx, s, temperature, weights, expected, *teachers):
         import ctypes
         _require_cuda(s, *teachers)
         K = len(teachers)
@@ -328,9 +440,10 @@ class _KdLossMulti(torch.autograd.Function):
         ptrs = (ctypes.c_void_p * K)(*[t.data_ptr() for t in ts])
         wts = (ctypes.c_float * K)(*[float(w) for w in weights])
         _abi.check(L.kdcc_kd_loss_multi(_ptr(s), ptrs, wts, K, _ptr(ds), _ptr(loss), _ptr(ws), ws.numel(), N, C, HW, bs, cs, ps,
-                                        float(temperature), _dtype_code(s), 1.0, _stream()), "kdcc_kd_loss_multi")
+                                        float(temperature), _dtype_code(s), float(expected), _stream()), "kdcc_kd_loss_multi")
         ctx.ds = ds
         ctx.K = K
+        ctx.expected = float(expected)
         return loss
 
     @staticmethod
@@ -338,24 +451,24 @@ class _KdLossMulti(torch.autograd.Function):
     def backward(ctx, g):
         ds = _take_grad(ctx)
         if ds is None:
-            return (None,) * (3 + ctx.K)
+            return (None,) * (4 + ctx.K)
         g = g.detach().float().contiguous()
-        _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
-                   "kdcc_scale_inplace")
-        return (ds,) + (None,) * (2 + ctx.K)
+        _abi.check(_abi.lib().kdcc_scale_inplace_expect(_ptr(ds), _ptr(g), ctx.expected, ds.numel(), _dtype_code(ds), _stream()),
+                   "kdcc_scale_inplace_expect")
+        return (ds,) + (None,) * (3 + ctx.K)
 
 
-def kd_loss_multi(inputs, teachers, weights, temperature=1.0):
+def kd_loss_multi(inputs, teachers, weights, temperature=1.0, expected_upstream=1.0):
     """sum_k weights[k] * T^2/(N*HW) * sum_pix KL(softmax(teachers[k]/T) || softmax(inputs/T)) in one pass over the
     student logits (trainer/ensemble_trainer.py:76-83); fp32 0-dim tensor with grad_fn."""
     teachers = list(teachers)
-    return _KdLossMulti.apply(inputs, float(temperature), tuple(float(w) for w in weights), *teachers)
+    return _KdLossMulti.apply(inputs, float(temperature), tuple(float(w) for w in weights), float(expected_upstream), *teachers)
 
 
 class _HintLoss(torch.autograd.Function):
     @staticmethod
     @_device_guard
-    def forward(ctx, s, t, weight, scale):
+    def forward(ctx, s, t, weight, scale, expected=1.0):
         _require_cuda(s, t, weight)
         if s.shape != t.shape or s.dim() < 2:
             raise _abi.KdccError("hint loss expects matching (N, C, ...) tensors, got %s and %s" % (tuple(s.shape), tuple(t.shape)))
@@ -383,8 +496,9 @@ class _HintLoss(torch.autograd.Function):
         L = _abi.lib()
         ws = _workspace(L.kdcc_loss_workspace_bytes() + 4 * N * C, s.device)
         _abi.check(L.kdcc_hint_loss(_ptr(s), _ptr(t), _ptr(w), per_sample, _ptr(ds), _ptr(loss), _ptr(ws), ws.numel(),
-                                    N, C, HW, layout, float(scale), _dtype_code(s), 1.0, _stream()), "kdcc_hint_loss")
+                                    N, C, HW, layout, float(scale), _dtype_code(s), float(expected), _stream()), "kdcc_hint_loss")
         ctx.ds = ds
+        ctx.expected = float(expected)
         return loss
 
     @staticmethod
@@ -392,16 +506,17 @@ class _HintLoss(torch.autograd.Function):
     def backward(ctx, g):
         ds = _take_grad(ctx)
         if ds is None:
-            return None, None, None, None
+            return None, None, None, None, None
         g = g.detach().float().contiguous()
-        _abi.check(_abi.lib().kdcc_scale_inplace(_ptr(ds), _ptr(g), ds.numel(), _dtype_code(ds), _stream()),
-                   "kdcc_scale_inplace")
-        return ds, None, None, None
+        _abi.check(_abi.lib().kdcc_scale_inplace_expect(_ptr(ds), _ptr(g), ctx.expected, ds.numel(), _dtype_code(ds), _stream()),
+                   "kdcc_scale_inplace_expect")
+        return ds, None, None, None, None
 
 
-def hint_loss(inputs, targets, filter_weight=None, scale=1.0):
-    """scale/N * sum_n [sum_c w mean_hw (s-t)^2 / sum_c w]; filter_weight None = uniform (MSELoss)."""
-    return _HintLoss.apply(inputs, targets, filter_weight, float(scale))
+def hint_loss(inputs, targets, filter_weight=None, scale=1.0, expected_upstream=1.0):
+    """scale/N * sum_n [sum_c w mean_hw (s-t)^2 / sum_c w]; filter_weight None = uniform (MSELoss).
+    `expected_upstream`: see kd_loss."""
+    return _HintLoss.apply(inputs, targets, filter_weight, float(scale), float(expected_upstream))
 
 
 # ---------------------------------------------------------------------------------------------------

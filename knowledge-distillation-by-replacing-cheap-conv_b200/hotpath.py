@@ -58,9 +58,18 @@ class HotPathStep:
         self.dtype, self.device = dtype, torch.device(device)
         self.code = _abi.F32 if dtype == torch.float32 else _abi.BF16
         self.T, self.nc, self.acc_steps = float(kd_temperature), float(hint_num_classes), int(accumulation_steps)
-        self.kd_grad, self.need_dx = kd_grad, need_dx
+        self.kd_grad = kd_grad
+        # per site: does the block's input need a gradient?  (a bool applies to every site; the first trainable conv of a
+        # network, fed by frozen layers only, does not -- SURVEY.md 3.4)
+        self.need_dx = [bool(need_dx)] * len(self.plan) if isinstance(need_dx, bool) else [bool(v) for v in need_dx]
         # "nchw" = the reference's layout -> tensor-core depthwise + W.X pointwise; "nhwc" = channels-last kernels
-        self.layout = _abi.NCHW if layout == "nchw" else _abi.NHWC
+        #   "nhwc" with a kernel larger than 3x3: channels_last INPUTS and OUTPUTS (what a cuDNN channels_last trunk hands over
+        #   and expects back), re-laid to channel planes at the block boundary so the depthwise stays on the tensor cores;
+        #   "nhwc_native": the NHWC CUDA-core kernels throughout
+        self.io_layout = _abi.NCHW if layout == "nchw" else _abi.NHWC
+        self.relayout = layout == "nhwc" and kernel_size > 3 and dtype == torch.bfloat16 and (height * width) % 8 == 0 and \
+            all(ci % 8 == 0 and co % 8 == 0 for ci, co in self.plan)
+        self.layout = _abi.NCHW if (layout == "nchw" or self.relayout) else _abi.NHWC
         self.L = _abi.lib()
         kk = kernel_size * kernel_size
 
@@ -93,9 +102,12 @@ class HotPathStep:
         # scratch shared by all sites (each site's forward+backward completes before the next starts)
         self.mid = e(cmax, self.Ho, self.Wo)
         self.dmid = e(cmax, self.Ho, self.Wo)
-        self.dx = e(cmax, height, width) if need_dx else None
+        self.dx = e(cmax, height, width) if any(self.need_dx) else None
         self.y = e(omax, self.Ho, self.Wo)
         self.dy = e(omax, self.Ho, self.Wo)
+        if self.relayout:  # channel-plane copies of what arrives / leaves channels_last
+            self.x_planes, self.y_cl, self.dy_cl = e(cmax, height, width), e(omax, self.Ho, self.Wo), e(omax, self.Ho, self.Wo)
+            self.dx_cl = e(cmax, height, width) if any(self.need_dx) else None
         # bf16 copy of the WHOLE flat parameter bucket, refreshed by one cast launch per step (the pointwise GEMMs read
         # their weights from it; one launch instead of one per site)
         self.flat_lp = torch.empty(total, dtype=dtype, device=self.device)
@@ -123,7 +135,7 @@ class HotPathStep:
             t = (torch.randn(shape, generator=g) * scale).to(dtype)
             return t.pin_memory() if pinned_host else t.to(self.device)
 
-        if self.layout == _abi.NCHW:
+        if self.io_layout == _abi.NCHW:
             xs = [rnd((self.N, ci, self.H, self.W), self.dtype) for ci, _ in self.plan]
             ts = [rnd((self.N, co, self.Ho, self.Wo), self.dtype) for _, co in self.plan]
         else:
@@ -164,23 +176,43 @@ class HotPathStep:
             if code == _abi.BF16:
                 a_, b_, c_ = self._views[i]
                 w_lp = self.flat_lp[b_:c_]
+            rl = self.relayout
+            if rl:   # channels_last input -> channel planes
+                chk(L.kdcc_layout_convert(_ptr(x), _ptr(self.x_planes), n, ci, H * W, 1, code, st), "relayout")
+                x = self.x_planes
+                mark("relayout")
+                launches += 1
             chk(L.kdcc_dw_fwd(_ptr(x), _ptr(w_dw), None, _ptr(self.mid), n, H, W, ci, k, d, p, lay, code, st), "dw_fwd")
             mark("dw_fwd")
             chk(L.kdcc_pw_fwd(_ptr(self.mid), _ptr(w_lp), None, None, 0, _ptr(self.y), None, M, ci, co, n, lay, code, st), "pw_fwd")
             mark("pw_fwd")
-            chk(L.kdcc_hint_loss(_ptr(self.y), _ptr(tf), None, 0, _ptr(self.dy), _ptr(self.hint_losses[i:]), ws, wsn,
-                                 n, co, Ho * Wo, lay, self.nc, code, 1.0 / self.acc_steps, st), "hint_loss")
+            y_io, dy_io = self.y, self.dy
+            if rl:   # the block's output leaves channels_last (the hint is taken against a channels_last teacher feature)
+                chk(L.kdcc_layout_convert(_ptr(self.y), _ptr(self.y_cl), n, co, Ho * Wo, 0, code, st), "relayout")
+                y_io, dy_io = self.y_cl, self.dy_cl
+                mark("relayout")
+                launches += 1
+            chk(L.kdcc_hint_loss(_ptr(y_io), _ptr(tf), None, 0, _ptr(dy_io), _ptr(self.hint_losses[i:]), ws, wsn,
+                                 n, co, Ho * Wo, self.io_layout, self.nc, code, 1.0 / self.acc_steps, st), "hint_loss")
             mark("hint_loss")
+            if rl:   # ... and its gradient arrives channels_last
+                chk(L.kdcc_layout_convert(_ptr(self.dy_cl), _ptr(self.dy), n, co, Ho * Wo, 1, code, st), "relayout")
+                mark("relayout")
+                launches += 1
             chk(L.kdcc_pw_bwd_dw(_ptr(self.dy), _ptr(self.mid), _ptr(g_pw), ws, wsn, M, ci, co, n, lay, code, st), "pw_bwd_dw")
             mark("pw_bwd_dw")
             chk(L.kdcc_pw_bwd_dx(_ptr(self.dy), _ptr(w_lp), _ptr(self.dmid), None, 0, M, ci, co, n, lay, code, st), "pw_bwd_dx")
             mark("pw_bwd_dx")
-            chk(L.kdcc_dw_bwd(_ptr(x), _ptr(w_dw), _ptr(self.dmid), _ptr(self.dx) if self.need_dx else None, _ptr(g_dw),
+            chk(L.kdcc_dw_bwd(_ptr(x), _ptr(w_dw), _ptr(self.dmid), _ptr(self.dx) if self.need_dx[i] else None, _ptr(g_dw),
                               None, ws, wsn, n, H, W, ci, k, d, p, lay, code, st), "dw_bwd")
             mark("dw_bwd")
+            if rl and self.need_dx[i]:   # the input gradient goes back channels_last
+                chk(L.kdcc_layout_convert(_ptr(self.dx), _ptr(self.dx_cl), n, ci, H * W, 0, code, st), "relayout")
+                mark("relayout")
+                launches += 1
             # dw_fwd 1, pw_fwd 1, hint 2 (pass + finalize), pw_dw 2 (gemm + split reduce), pw_dx 1,
             # dw_bwd: wgrad 1 + reduce 1 (+ dx conv 1)
-            launches += 1 + 1 + 2 + 2 + 1 + (3 if self.need_dx else 2)
+            launches += 1 + 1 + 2 + 2 + 1 + (3 if self.need_dx[i] else 2)
         if logits_s is not None:
             N_, C_ = logits_s.shape[0], logits_s.shape[1]
             HW = logits_s.numel() // (N_ * C_)
@@ -210,20 +242,22 @@ class HotPathStep:
         """{kernel: (bytes_or_flops_per_step, 'B'|'FLOP')} summed over the sites of one step."""
         es = 4 if self.dtype == torch.float32 else 2
         P_in, P_out, n, kk = self.H * self.W, self.Ho * self.Wo, self.N, self.k * self.k
-        out = {"dw_fwd": 0, "dw_bwd": 0, "pw_fwd": 0, "pw_bwd_dx": 0, "pw_bwd_dw": 0, "hint_loss": 0, "kd_loss": 0}
-        for ci, co in self.plan:
+        out = {"dw_fwd": 0, "dw_bwd": 0, "pw_fwd": 0, "pw_bwd_dx": 0, "pw_bwd_dw": 0, "hint_loss": 0, "kd_loss": 0, "relayout": 0}
+        for i, (ci, co) in enumerate(self.plan):
             out["dw_fwd"] += n * (P_in + P_out) * ci * es + ci * kk * 4
-            out["dw_bwd"] += n * (P_in + P_out + (P_in if self.need_dx else 0)) * ci * es + ci * kk * 4
+            out["dw_bwd"] += n * (P_in + P_out + (P_in if self.need_dx[i] else 0)) * ci * es + ci * kk * 4
             flops = 2 * n * P_out * ci * co
             out["pw_fwd"] += flops
             out["pw_bwd_dx"] += flops
             out["pw_bwd_dw"] += flops
             out["hint_loss"] += 3 * n * P_out * co * es
+            if self.relayout:   # x in, y out, dy in (read + write each), dx out where it exists
+                out["relayout"] += 2 * es * n * (P_in * ci * (2 if self.need_dx[i] else 1) + 2 * P_out * co)
         if self.logits_shape:
             numel = 1
             for s_ in self.logits_shape:
                 numel *= s_
             out["kd_loss"] = (3 if self.kd_grad else 2) * numel * 4
-        units = {"dw_fwd": "B", "dw_bwd": "B", "hint_loss": "B", "kd_loss": "B",
+        units = {"dw_fwd": "B", "dw_bwd": "B", "hint_loss": "B", "kd_loss": "B", "relayout": "B",
                  "pw_fwd": "FLOP", "pw_bwd_dx": "FLOP", "pw_bwd_dw": "FLOP"}
         return {k_: (v, units[k_]) for k_, v in out.items()}

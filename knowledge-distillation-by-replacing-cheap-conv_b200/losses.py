@@ -7,6 +7,11 @@ from torch import nn
 
 from . import functional as F_kdcc
 
+# Every criterion carries `expected_upstream` (default 1.0): the value its backward expects from autograd -- 1 for
+# `loss.backward()`, 1 / accumulation_steps inside the layerwise loop (kdcc.LayerwiseStep sets it).  It is folded into the
+# gradient the fused forward kernel emits and verified on the device in backward (rescaled there if it turns out to
+# differ), which removes a full read-modify-write pass over the gradient from every backward.  Not a reference argument.
+
 
 class KLDivergenceLoss(nn.Module):
     """losses/KLDiv.py:4-23 -- kl_div(log_softmax(s/T), softmax(t/T)) * T^2 * C, 'mean' over all elements."""
@@ -14,9 +19,10 @@ class KLDivergenceLoss(nn.Module):
     def __init__(self, temperature=1):
         super().__init__()
         self.temperature = temperature
+        self.expected_upstream = 1.0
 
     def forward(self, inputs, targets):
-        return F_kdcc.kd_loss(inputs, targets, self.temperature, target_is_prob=False)
+        return F_kdcc.kd_loss(inputs, targets, self.temperature, target_is_prob=False, expected_upstream=self.expected_upstream)
 
 
 class EnsembleKLDivergenceLoss(nn.Module):
@@ -24,9 +30,10 @@ class EnsembleKLDivergenceLoss(nn.Module):
 
     def __init__(self):
         super().__init__()
+        self.expected_upstream = 1.0
 
     def forward(self, inputs, targets):
-        return F_kdcc.kd_loss(inputs, targets, 1.0, target_is_prob=True)
+        return F_kdcc.kd_loss(inputs, targets, 1.0, target_is_prob=True, expected_upstream=self.expected_upstream)
 
 
 class MSELoss(nn.Module):
@@ -38,9 +45,10 @@ class MSELoss(nn.Module):
             raise ValueError("kdcc MSELoss implements reduction='mean' (the only value the reference configs use)")
         self.reduction = reduction
         self.num_classes = num_classes
+        self.expected_upstream = 1.0
 
     def forward(self, inputs, targets):
-        return F_kdcc.hint_loss(inputs, targets, None, scale=float(self.num_classes))
+        return F_kdcc.hint_loss(inputs, targets, None, scale=float(self.num_classes), expected_upstream=self.expected_upstream)
 
 
 class WeightedHintMSELoss(nn.Module):
@@ -51,9 +59,10 @@ class WeightedHintMSELoss(nn.Module):
         super().__init__()
         self.reduction = reduction
         self.num_classes = num_classes
+        self.expected_upstream = 1.0
 
     def forward(self, inputs, targets, filter_weight):
-        return F_kdcc.hint_loss(inputs, targets, filter_weight, scale=1.0)
+        return F_kdcc.hint_loss(inputs, targets, filter_weight, scale=1.0, expected_upstream=self.expected_upstream)
 
 
 class MultiTeacherKLDivergenceLoss(nn.Module):
@@ -66,6 +75,7 @@ class MultiTeacherKLDivergenceLoss(nn.Module):
         super().__init__()
         self.temperature = temperature
         self.weight = weight  # WEIGHT of trainer/ensemble_trainer.py:10
+        self.expected_upstream = 1.0
 
     def forward(self, inputs, ensemble_outputs, teacher_output=None):
         outs = list(ensemble_outputs)
@@ -74,4 +84,4 @@ class MultiTeacherKLDivergenceLoss(nn.Module):
             outs.append(teacher_output)
             w.append(1.0)
         total = sum(w)
-        return F_kdcc.kd_loss_multi(inputs, outs, [x / total for x in w], self.temperature)
+        return F_kdcc.kd_loss_multi(inputs, outs, [x / total for x in w], self.temperature, expected_upstream=self.expected_upstream)

@@ -12,6 +12,7 @@ import torch
 from torch.optim.optimizer import Optimizer
 
 from . import _abi
+from .functional import lp_copy_of, lp_refreshed
 
 
 class RAdam(Optimizer):
@@ -75,8 +76,16 @@ class RAdam(Optimizer):
                 n_sma, size = self.step_scalars(state['step'], beta1, beta2)
                 mode = 0 if n_sma >= 5 else (1 if size > 0 else 2)
                 lp = self._lp.get(p)
+                cached = None
+                if lp is None:   # a bf16 copy some forward made of this master weight: refresh it in the same pass
+                    lp = cached = lp_copy_of(p)
                 _abi.check(L.kdcc_radam_step(p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(), state['exp_avg_sq'].data_ptr(),
                                              lp.data_ptr() if lp is not None else None, p.numel(), beta1, beta2, 1 - beta1, 1 - beta2, group['eps'],
                                              -group['weight_decay'] * group['lr'], -size * group['lr'], mode,
                                              torch.cuda.current_stream(p.device).cuda_stream), "kdcc_radam_step")
+                # the kernel wrote p through a raw pointer: move its version counter like an in-place op would, so autograd's
+                # saved-tensor checks and the weight-copy cache see the update
+                torch.autograd.graph.increment_version(p)
+                if cached is not None:
+                    lp_refreshed(p)
         return loss

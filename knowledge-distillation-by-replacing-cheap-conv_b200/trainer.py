@@ -55,6 +55,13 @@ class GradBucket:
                 self.flat.div_(world)
 
 
+def _expect(criterion, value):
+    """Tell a kdcc criterion which upstream gradient its backward will see (a device-verified performance hint, see
+    kdcc.losses); anything that is not a kdcc criterion is left alone."""
+    if hasattr(criterion, "expected_upstream"):
+        criterion.expected_upstream = float(value)
+
+
 class LayerwiseStep:
     """criterions = [supervised, kd, hint] as in train.py:48-50; `model` is a DepthwiseStudent."""
 
@@ -64,6 +71,7 @@ class LayerwiseStep:
         self.group = process_group
         self.log_supervised = log_supervised
         self.bucket = GradBucket(model.trainable_parameters())
+        _expect(criterions[2], 1.0 / self.accumulation_steps)   # loss = sum(hint pairs) / accumulation_steps
 
     def rebuild_bucket(self):
         self.bucket = GradBucket(self.model.trainable_parameters())
@@ -104,6 +112,7 @@ class ClassificationStep:
         self.accumulation_steps = int(accumulation_steps)
         self.group = process_group
         self.bucket = GradBucket(model.trainable_parameters())
+        _expect(criterions[1], 1.0 / self.accumulation_steps)   # loss = kd / accumulation_steps
 
     def rebuild_bucket(self):
         self.bucket = GradBucket(self.model.trainable_parameters())

@@ -76,6 +76,7 @@ def test_block_bf16_matches_reference_golden(kdcc, golden_block, tag, mode, monk
     # the tma* modes switch the streaming 3x3 kernels off so that the TMA-staged k=3 configuration stays covered
     monkeypatch.setenv("KDCC_DW_MODE", {"tma_plain_load": "1", "tma_plain_store": "2"}.get(mode, "0"))
     monkeypatch.setenv("KDCC_DW_FORCE_DIRECT", "1" if mode == "direct" else "0")
+    monkeypatch.setenv("KDCC_DW_KEEP_NHWC", "1")   # NHWC kernels under test: no re-layout to the NCHW tensor-core path
     if mode.startswith("tma"):
         monkeypatch.setenv("KDCC_DW_NHWC3_OFF", "1")
     g = golden_block
@@ -111,7 +112,8 @@ SEEDED = [
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("geom", SEEDED)
-def test_block_matches_oracle_seeded(kdcc, geom, dtype):
+def test_block_matches_oracle_seeded(kdcc, geom, dtype, monkeypatch):
+    monkeypatch.setenv("KDCC_DW_KEEP_NHWC", "1")   # these cases are about the NHWC kernels: no re-layout to the NCHW path
     N, Ci, Co, H, W, k, d, p = geom
     rs = np.random.RandomState(1234 + Ci + H)
     x = rs.standard_normal((N, Ci, H, W)).astype(np.float32)

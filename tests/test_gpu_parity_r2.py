@@ -156,3 +156,95 @@ def test_radam_steps_through_a_bucket_with_odd_sized_parameters(kdcc):
         assert torch.allclose(p.detach().cpu(), e, rtol=1e-5, atol=1e-6)
     bucket.zero()
     assert all(float(p.grad.abs().sum()) == 0 for p in params)
+
+
+def test_expected_upstream_is_a_hint_not_an_assumption(kdcc):
+    """The loss kernels fold the upstream gradient a caller expects into the gradient they emit; backward verifies it on
+    the device.  Whether the hint is right (no memory traffic in backward) or wrong (rescaled), ds is the same."""
+    torch.manual_seed(1)
+    t = torch.randn(2, 16, 8, 8, device="cuda")
+    grads = []
+    for expected, divide in ((1.0, 4.0), (0.25, 4.0), (0.25, 1.0), (3.0, 7.0)):
+        s = torch.randn(2, 16, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(5)).requires_grad_(True)
+        crit = kdcc.MSELoss(num_classes=1000)
+        crit.expected_upstream = expected
+        (crit(s, t) / divide).backward()
+        grads.append(s.grad * divide)
+    for g in grads[1:]:
+        assert torch.allclose(g, grads[0], rtol=1e-6, atol=0)
+    s = torch.randn(2, 19, 8, 8, device="cuda", requires_grad=True)
+    tt = torch.randn(2, 19, 8, 8, device="cuda")
+    a = kdcc.functional.kd_loss(s, tt, 2.0, expected_upstream=1.0)
+    a.backward()
+    ga, s.grad = s.grad.clone(), None
+    (kdcc.functional.kd_loss(s, tt, 2.0, expected_upstream=0.5) * 1.0).backward()
+    assert torch.allclose(s.grad, ga, rtol=1e-6, atol=0)
+
+
+def test_cached_bf16_weight_copy_follows_the_master_weight(kdcc):
+    """pointwise_conv caches the bf16 copy of its fp32 master weight by the parameter's version counter: an in-place torch
+    update invalidates it, and kdcc.optim.RAdam refreshes it inside its fused step (no cast launch afterwards)."""
+    torch.manual_seed(2)
+    x = torch.randn(2, 64, 8, 8, device="cuda").to(torch.bfloat16)
+    w = torch.nn.Parameter(torch.randn(32, 64, 1, 1, device="cuda") / 8)
+    ref = lambda: torch.nn.functional.conv2d(x.float(), w.detach().to(torch.bfloat16).float())
+    y0 = kdcc.functional.pointwise_conv(x, w)
+    assert relerr(host(y0), host(ref())) < TOL[torch.bfloat16]
+    lp0 = kdcc.functional.lp_copy_of(w)
+    assert lp0 is not None and kdcc.functional.lp_weight(w, torch.bfloat16) is lp0          # reused while w is unchanged
+    with torch.no_grad():
+        w.mul_(-2.0)                                                                         # torch in-place op: version moves
+    y1 = kdcc.functional.pointwise_conv(x, w)
+    assert relerr(host(y1), host(ref())) < TOL[torch.bfloat16] and relerr(host(y1), -2 * host(y0)) < 2e-2
+    opt = kdcc.optim.RAdam([w], lr=0.1)
+    w.grad = torch.ones_like(w)
+    lp1 = kdcc.functional.lp_copy_of(w)
+    opt.step()                                                                               # rewrites w AND its cached copy
+    assert kdcc.functional.lp_weight(w, torch.bfloat16) is lp1
+    torch.cuda.synchronize()
+    assert torch.equal(lp1.float(), w.detach().to(torch.bfloat16).float())
+    y2 = kdcc.functional.pointwise_conv(x, w)
+    assert relerr(host(y2), host(ref())) < TOL[torch.bfloat16]
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 24), (1, 72, 5, 8), (3, 8, 128, 128), (2, 4096, 8, 16), (1, 200, 9, 40)])
+def test_layout_convert_is_a_bit_exact_transpose(kdcc, shape):
+    """kdcc_layout_convert (the channels_last <-> NCHW re-layout at a block boundary): exact, both directions, ragged tiles."""
+    N, C, H, W = shape
+    L = kdcc._abi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(N, C, H, W, device="cuda").to(torch.bfloat16)                        # NCHW-physical
+    cl = torch.empty_like(x, memory_format=torch.channels_last)
+    kdcc._abi.check(L.kdcc_layout_convert(x.data_ptr(), cl.data_ptr(), N, C, H * W, 0, kdcc._abi.BF16, st), "to nhwc")
+    assert torch.equal(cl, x) and cl.is_contiguous(memory_format=torch.channels_last)
+    back = torch.empty(N, C, H, W, device="cuda", dtype=torch.bfloat16)
+    kdcc._abi.check(L.kdcc_layout_convert(cl.data_ptr(), back.data_ptr(), N, C, H * W, 1, kdcc._abi.BF16, st), "to nchw")
+    assert torch.equal(back, x) and back.is_contiguous()
+    assert L.kdcc_layout_convert(x.data_ptr(), cl.data_ptr(), N, C + 1, H * W, 0, kdcc._abi.BF16, st) != 0   # C % 8 != 0: refused
+
+
+@pytest.mark.parametrize("geom", [(2, 64, 128, 40, 40, 9, 5, 20), (1, 512, 512, 128, 128, 9, 5, 20), (3, 24, 8, 37, 40, 9, 5, 20)])
+def test_channels_last_block_runs_on_the_tensor_core_path_and_returns_channels_last(kdcc, geom):
+    """A channels_last (cuDNN-style) trunk around the block: the k = 9 depthwise is re-laid to channel planes at the block
+    boundary, runs on the NCHW tensor-core kernels, and output / input gradient come back channels_last."""
+    from test_gpu_parity import oracle_block
+    N, Ci, Co, H, W, k, d, p = geom
+    dtype = torch.bfloat16
+    rs = np.random.RandomState(99 + Ci + H)
+    x = rs.standard_normal((N, Ci, H, W)).astype(np.float32)
+    w_dw = (rs.uniform(-1, 1, (Ci, 1, k, k)) / k).astype(np.float32)
+    w_pw = (rs.uniform(-1, 1, (Co, Ci, 1, 1)) / np.sqrt(Ci)).astype(np.float32)
+    dy = rs.standard_normal((N, Co, H, W)).astype(np.float32)
+    blk = kdcc.DepthwiseSeparableBlock(Ci, Co, k, p, d, Ci, None).cuda()
+    with torch.no_grad():
+        blk.separable_conv.weight.copy_(torch.from_numpy(w_dw))
+        blk.pointwise_conv.weight.copy_(torch.from_numpy(w_pw))
+    xt = torch.from_numpy(x).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = blk(xt)
+    assert y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous()
+    y.backward(torch.from_numpy(dy).cuda().to(dtype).contiguous(memory_format=torch.channels_last))
+    assert xt.grad.is_contiguous(memory_format=torch.channels_last)
+    ry, rdx, rdwd, rdwp = oracle_block(x, w_dw, w_pw, dy, k, d, p, dtype)
+    for name, mine, ref in (("y", host(y), ry), ("dx", host(xt.grad), rdx), ("dw_dw", host(blk.separable_conv.weight.grad), rdwd),
+                            ("dw_pw", host(blk.pointwise_conv.weight.grad), rdwp)):
+        assert relerr(mine, ref) < TOL[dtype], name
