@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--api-steps", type=int, default=10, help="timed steps of the drop-in modules-API run")
     ap.add_argument("--whole-steps", type=int, default=6, help="timed steps of the whole-step run with the DeepLabV3+ trunk (0 = skip)")
     ap.add_argument("--trunk-format", default="channels_last", choices=["nchw", "channels_last"], help="memory format of the harness trunk")
+    ap.add_argument("--grad-exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = gradients pushed into every peer's symmetric buffer by copy engines while the backward runs, "
+                         "mean taken inside the fused RAdam pass (kdcc.PeerGradBucket); nccl = one NCCL all-reduce (AVG) after the backward")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch.optim.RAdam + a separate weight cast instead of the fused kdcc RAdam step")
     ap.add_argument("--graph", action="store_true",
                     help="replay a CUDA graph of the pass instead of stream launches (measured: 475.8 vs 474.5 img/s, i.e. the "
@@ -140,19 +143,31 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------------
 # reference / CPU arm: the reference's own calls (torch CPU backend) restated in oracle/torch_port.py
 # -------------------------------------------------------------------------------------------------------
-def tensor_issue_floor(plan, batch, geom, layout, maps, measured_ms, sm_mhz, sms=148):
-    """What the measured MMA cost model (tools/mma_probe.cu) says the whole-plane tensor-core depthwise
-    backward (dX conv + dW) cannot go below: per 128 x 128 plane 2*d*k MMAs of 43 + 32/2 = 59 clk for the conv and
-    k * 8 MMAs of 10 + 128/2 = 74 clk for the weight gradient, one plane per SM at a time, at the sampled SM clock.
-    Only defined for the geometry those kernels cover; returns None otherwise."""
+# Shared-memory bytes one 128 x 128 plane moves through an SM's 128 B/clk shared-memory / L1 data path in the whole-plane
+# tensor-core depthwise kernels (measured rates: tools/tc_probe2.cu -> profiles/r02_tc_probe2.txt):
+#   conv (dw_tc2.cu): 90 SS MMAs x (4 KB image slab + 1 KB Toeplitz chunk) = 450 KB of operand reads, TMA landing 32 KB,
+#     regrouping 32 KB read + 40 KB written, epilogue staging 32 KB written + 32 KB read by the TMA store        = 618 KB
+#   dW (dw_tc_wgrad2.cu): 72 TS MMAs x 4 KB of B = 288 KB, TMA landing 64 KB, dy transposition (2-byte reads use half a
+#     wavefront: 64 KB), diagonal extraction through the scratch rows (write 180 KB + read 52 KB)                  = 648 KB
+SMEM_BYTES_PER_PLANE = {"conv": 618 * 1024, "wgrad": 648 * 1024}
+SMEM_BYTES_PER_CLK = 128
+
+
+def smem_floor(plan, batch, geom, layout, maps, need_dx, measured_ms, sm_mhz, sms=148):
+    """Lower bound of the depthwise backward (dX conv + dW) from the bytes its kernels move through shared memory:
+    planes x bytes per plane / (128 B/clk) / 148 SMs at the sampled SM clock.  This -- not HBM, and not tensor-core math
+    (90 x 16 clk for the conv) -- is what bounds the k = 9 kernels: tcgen05.mma with both operands in shared memory
+    streams them at the same 128 B/clk the rest of the kernel uses (an M=128 N=32 K=16 MMA takes 40 clk = 5 KB / 128).
+    Only defined for the geometry the whole-plane kernels cover; returns None otherwise."""
     k, d, p = geom
-    if layout != "nchw" or maps > 128 or p % d != 0 or not sm_mhz or not measured_ms:
+    if layout != "nchw" or maps > 128 or p % d != 0 or not sm_mhz or not measured_ms or (k, d) != (9, 5):
         return None
-    planes = batch * sum(ci for ci, _ in plan)
-    clk = planes * (2 * d * k * 59 + k * 8 * 74) / float(sms)
+    planes_dw = batch * sum(ci for ci, _ in plan)
+    planes_dx = batch * sum(ci for (ci, _), nd in zip(plan, need_dx) if nd)
+    clk = (planes_dx * SMEM_BYTES_PER_PLANE["conv"] + planes_dw * SMEM_BYTES_PER_PLANE["wgrad"]) / float(SMEM_BYTES_PER_CLK) / sms
     floor_ms = clk / (sm_mhz * 1e3)
     return {"ms": round(floor_ms, 3), "frac": round(floor_ms / measured_ms, 4), "sm_mhz": sm_mhz,
-            "model": "planes x (2*d*k x 59 clk conv + 8*k x 74 clk dW) / %d SMs" % sms}
+            "model": "(%d dX planes x 618 KB + %d dW planes x 648 KB) / 128 B/clk / %d SMs" % (planes_dx, planes_dw, sms)}
 
 
 def cpu_reference_image_seconds(plan, maps, geom, budget_s, crop):
@@ -291,8 +306,8 @@ def api_modules_run(plan, batch, maps, geom, crop, dev, world, steps, seed):
     torch.manual_seed(seed)
     blocks = [kdcc.DepthwiseSeparableBlock(ci, co, k, p, d, ci, None).to(dev) for ci, co in plan]
     params = [prm for b in blocks for prm in b.parameters()]
-    bucket = kdcc.GradBucket(params)
     opt = kdcc.optim.RAdam(params, lr=5e-3)
+    bucket = kdcc.GradBucket(params, peer=world > 1, optimizer=opt)   # N > 1: peer pushes during the backward, mean in the RAdam pass
     hint_crit, kd_crit = kdcc.MSELoss(num_classes=1000), kdcc.KLDivergenceLoss(temperature=1)
     # the first replaced conv's input comes from frozen layers only: no input gradient
     xs = [torch.randn(batch, ci, maps, maps, device=dev).to(torch.bfloat16).requires_grad_(i > 0) for i, (ci, _) in enumerate(plan)]
@@ -563,6 +578,22 @@ def run_kdcc(args, rank, world, local_rank):
             hp.refresh_lp()
             hp.lp_maintained = True
 
+    # N > 1: how the student gradients are averaged over the ranks
+    peer, exchange = None, "none"
+    if world > 1:
+        exchange = "nccl all-reduce (AVG) of the flat fp32 bucket after the backward"
+        if args.grad_exchange == "peer" and not args.torch_optimizer and not args.graph:
+            try:
+                peer = kdcc.PeerGradBucket(hp.flat_grads.numel(), dev)
+                hp.flat_grads = peer.local()
+                param.grad = hp.flat_grads
+                opt.attach_grad_sources(param, peer.sources)
+                exchange = ("per-site copy-engine pushes into every peer's symmetric buffer during the backward; mean of the %d copies "
+                            "taken inside the fused RAdam pass (no collective kernel)" % world)
+            except Exception as exc:
+                peer = None
+                exchange += " [peer exchange unavailable: %s]" % (repr(exc)[:120],)
+
     # --graph: the 97 libkdcc launches of one pass are captured once into a CUDA graph and replayed; the all-reduce and
     # the optimizer stay ordinary stream work; CUDA events recorded inside the capture give the per-kernel timeline of
     # the last replay.  Default: plain stream launches (the CPU enqueues a step in ~5.5 ms and runs ahead of the GPU).
@@ -577,12 +608,20 @@ def run_kdcc(args, rank, world, local_rank):
             if log is not None:
                 log.mark("begin")
         else:
-            hint, kd = hp.step(xs, ts, ls, lt, log=log)
-        if world > 1:
+            hint, kd = hp.step(xs, ts, ls, lt, log=log, site_done=peer.push if peer is not None else None)
+        if peer is not None:
+            peer.finish()
+            if log is not None:
+                log.mark("grad_allreduce")      # here: waiting for the last pushes (own and peers') to land
+        elif world > 1:
             dist.all_reduce(hp.flat_grads, op=dist.ReduceOp.AVG)
             if log is not None:
                 log.mark("grad_allreduce")
         opt.step()
+        if peer is not None:                    # next step writes the other parity of the symmetric buffer
+            peer.flip()
+            hp.flat_grads = peer.local()
+            param.grad = hp.flat_grads
         if log is not None:
             log.mark("optimizer")
         return hint, kd
@@ -665,10 +704,16 @@ def run_kdcc(args, rank, world, local_rank):
                     issue_copy(i + 1)
                 main.wait_event(copied[i & 1])
                 dx, dt, dls, dlt = sets[i & 1]
-                h_, k_ = hp.step(dx, dt, dls, dlt)
-                if world > 1:
+                h_, k_ = hp.step(dx, dt, dls, dlt, site_done=peer.push if peer is not None else None)
+                if peer is not None:
+                    peer.finish()
+                elif world > 1:
                     dist.all_reduce(hp.flat_grads, op=dist.ReduceOp.AVG)
                 opt.step()
+                if peer is not None:
+                    peer.flip()
+                    hp.flat_grads = peer.local()
+                    param.grad = hp.flat_grads
                 consumed[i & 1].record(main)
                 out_host.copy_(torch.stack([h_, k_]), non_blocking=True)
 
@@ -757,8 +802,9 @@ def run_kdcc(args, rank, world, local_rank):
     if dominant.startswith("dw") and k >= 7:
         note = ("achieved = algorithmic bytes of all %d launches of one step / their CUDA-event time; traffic = ncu DRAM bytes of the "
                 "same launches.  k=9 depthwise is 81 MAC per output element (20 MAC per HBM byte): the kernels run on tcgen05 and are "
-                "bound by the issue cost of their small-N MMAs (90 x 59 clk conv, 72 x 74 clk dW per plane, DESIGN.md 4.0/4.1), "
-                "not by HBM; frac is still reported against the HBM copy peak" % dk["launches_per_step"])
+                "bound by the 128 B/clk shared-memory data path that feeds the MMAs (618 KB per plane for the conv, 648 KB for dW: "
+                "smem_floor; DESIGN.md 4.0/4.1), not by HBM; frac is still reported against the HBM copy peak.  Against the stock "
+                "torch CUDA kernels for the same call the family is ~50x faster (gpu_baseline)" % dk["launches_per_step"])
     roofline = {"kernel": dominant, "bound": dk["bound"], "achieved": dk["achieved"],
                 "peak": pk["hbm_gbs"] if dk["bound"] == "hbm" else pk["bf16_tflops"], "unit": dk["unit"],
                 "frac": dk["frac"], "traffic": traffic, "algorithmic_bytes": alg[dominant][0] if alg[dominant][1] == "B" else None,
@@ -766,8 +812,8 @@ def run_kdcc(args, rank, world, local_rank):
                 "note": note}
     try:  # the resource that actually binds the dominant family (an annotation: it must never break the line)
         if dominant == "dw_bwd" and k >= 7:
-            roofline["tensor_issue_floor"] = tensor_issue_floor(plan, N, (k, d, p), args.layout, maps, dk["ms_per_step"],
-                                                                (clocks or {}).get("sm_mhz"))
+            roofline["smem_floor"] = smem_floor(plan, N, (k, d, p), args.layout, maps, need_dx, dk["ms_per_step"],
+                                                (clocks or {}).get("sm_mhz"))
     except Exception:
         pass
 
@@ -831,6 +877,39 @@ def run_kdcc(args, rank, world, local_rank):
         except Exception as exc:
             kernels_k3 = {"error": repr(exc)[:200]}
 
+    # ---- BASELINE config 4: the same nine block names in the Gated-SCNN teacher on a 1024 x 2048 input (128 x 256 maps),
+    #      KLDiv on the logits + WeightedHintMSE with a per-channel weight vector; per-GPU batch 2 ----
+    kernels_gscnn = None
+    if not args.no_extras and world == 1 and (k, d, p) == (9, 5, 20) and args.layout == "nchw":
+        try:
+            torch.cuda.empty_cache()
+            hg = HotPathStep(plan, 2, 128, 256, 9, 5, 20, dtype=torch.bfloat16, device=dev, logits_shape=(2, 19, 1024, 2048), need_dx=need_dx,
+                             seed=9, layout="nchw", hint_weighted=True)
+            xg, tg, lsg, ltg = hg.make_inputs(seed=13)
+            for _ in range(3):
+                hg.step(xg, tg, lsg, ltg)
+            lg = EventLog()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(5):
+                hg.step(xg, tg, lsg, ltg, log=lg)
+            g1.record()
+            torch.cuda.synchronize()
+            dg, ag = lg.durations_ms(), hg.algorithmic()
+            kernels_gscnn = {"img_per_s": round(2 * 5 / (g0.elapsed_time(g1) * 1e-3), 1), "ms_per_step": round(g0.elapsed_time(g1) / 5, 3),
+                             "note": "cfg/cityscapes/51M_gscnn_all.json shapes: 9 sites on 128x256 maps (1024x2048 input), batch 2, k9 d5 p20, "
+                                     "WeightedHintMSELoss with a weight vector, KLDiv on (2,19,1024,2048); planes wider than 128 columns run "
+                                     "the tiled Toeplitz kernels (dw_tc.cu / dw_tc_wgrad.cu)"}
+            for n_ in ("dw_fwd", "dw_bwd", "pw_fwd", "pw_bwd_dx", "pw_bwd_dw", "hint_loss", "kd_loss"):
+                ms_ = sum(dg[n_]) / 5
+                unit_ = ag[n_][1]
+                kernels_gscnn[n_] = {"ms_per_step": round(ms_, 4), "achieved": round(ag[n_][0] / (ms_ * 1e-3) / (1e9 if unit_ == "B" else 1e12), 1),
+                                     "unit": "GB/s" if unit_ == "B" else "TFLOP/s"}
+            del hg, xg, tg, lsg, ltg
+        except Exception as exc:
+            kernels_gscnn = {"error": repr(exc)[:200]}
+
     line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -838,9 +917,10 @@ def run_kdcc(args, rank, world, local_rank):
                            launch=("CUDA graph of the pass replayed per step; per-kernel times = CUDA events inside the graph, last timed step"
                                    if use_graph else "stream launches; per-kernel times = CUDA events between launches, all timed steps"),
                            cache="inputs larger than L2 (per-step working set of several GB >> 126 MB), no explicit flush"),
+            "grad_exchange": exchange,
             "clocks": clocks, "e2e": e2e, "gpu_launches": (hp.launches_per_step + (0 if args.torch_optimizer else 1)) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline, "api_modules": api, "whole_step": whole, "scaling_diag": scaling_diag,
-            "kernels": kernels, "kernels_k3": kernels_k3, "losses": {"hint": float(hint), "kd": float(kd)}}
+            "kernels": kernels, "kernels_k3": kernels_k3, "kernels_gscnn": kernels_gscnn, "losses": {"hint": float(hint), "kd": float(kd)}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -178,6 +178,12 @@ int kdcc_confusion_update(const void *logits, const long long *labels, long long
 int kdcc_radam_step(float *p, const float *g, float *m, float *v, void *p_lp, long n, float beta1, float beta2,
                     float one_minus_beta1, float one_minus_beta2, float eps, float decay, float step, int mode,
                     kdcc_stream_t stream);
+/* Data-parallel form: g points at n_src copies of the gradient, src_stride floats apart (one per rank, written into this
+ * rank's memory by its peers); the step uses their mean, summed in source order (bit-identical on every rank).  The gradient
+ * all-reduce of the layerwise loop fused into the optimizer pass. */
+int kdcc_radam_step_multi(float *p, const float *g, long src_stride, int n_src, float *m, float *v, void *p_lp, long n,
+                          float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps, float decay,
+                          float step, int mode, kdcc_stream_t stream);
 
 /* ---- sliding-window test-time inference -------------------------------------------
  * kdcc_tta_stitch replaces utils/tta_process.py:39-52 (collect_windows_result) and the np.fliplr of :19-20:

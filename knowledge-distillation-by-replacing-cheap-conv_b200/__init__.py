@@ -12,6 +12,7 @@ from . import checkpoint, functional, optim, tta
 from .student import DepthwiseStudent
 from .metrics import CityscapesMetricTracker, ConfusionMatrix
 from .trainer import ClassificationStep, EnsembleStep, GradBucket, LayerwiseStep, prepare_train_epoch
+from .peer_reduce import PeerGradBucket
 
-__all__ = ["DepthwiseSeparableBlock", "DepthwiseStudent", "LayerwiseStep", "ClassificationStep", "EnsembleStep", "GradBucket", "prepare_train_epoch", "ConfusionMatrix", "CityscapesMetricTracker", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MultiTeacherKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
+__all__ = ["DepthwiseSeparableBlock", "DepthwiseStudent", "LayerwiseStep", "ClassificationStep", "EnsembleStep", "GradBucket", "PeerGradBucket", "prepare_train_epoch", "ConfusionMatrix", "CityscapesMetricTracker", "KLDivergenceLoss", "EnsembleKLDivergenceLoss", "MultiTeacherKLDivergenceLoss", "MSELoss", "WeightedHintMSELoss",
            "functional", "checkpoint", "KdccError", "LIB_PATH"]

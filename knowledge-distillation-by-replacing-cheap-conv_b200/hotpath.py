@@ -49,7 +49,7 @@ class EventLog:
 class HotPathStep:
     def __init__(self, plan, batch, height, width, kernel_size=9, dilation=5, padding=20, dtype=torch.bfloat16,
                  device="cuda", logits_shape=None, kd_temperature=1.0, hint_num_classes=1000.0,
-                 accumulation_steps=1, kd_grad=False, need_dx=True, seed=0, layout="nchw"):
+                 accumulation_steps=1, kd_grad=False, need_dx=True, seed=0, layout="nchw", hint_weighted=False):
         self.plan = list(plan)
         self.N, self.H, self.W = batch, height, width
         self.k, self.d, self.p = kernel_size, dilation, padding
@@ -118,6 +118,14 @@ class HotPathStep:
                            self.L.kdcc_pw_bwd_workspace_bytes(1, M, ci, co, self.code))
         self.ws = torch.empty(ws_bytes + 64, dtype=torch.uint8, device=self.device)
         self.hint_losses = torch.zeros(len(self.plan), dtype=torch.float32, device=self.device)
+        # hint_weighted: losses/WeightedHintMSELoss.py (per-channel filter weights, e.g. normalised Taylor importances --
+        # utils/util.py:191-216) instead of losses/MSELoss.py * num_classes
+        self.hint_w = None
+        if hint_weighted:
+            gw = torch.Generator(device="cpu").manual_seed(seed + 17)
+            self.hint_w = [torch.rand(co, generator=gw).to(self.device) for _, co in self.plan]
+            ws_bytes += 4 * batch * omax
+            self.ws = torch.empty(ws_bytes + 64, dtype=torch.uint8, device=self.device)
         self.kd_loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self.logits_shape = logits_shape
         self.dlogits = torch.empty(logits_shape, dtype=torch.float32, device=self.device) if (logits_shape and kd_grad) else None
@@ -155,8 +163,10 @@ class HotPathStep:
         a, b, c = self._views[i]
         return self.flat_params[a:b], self.flat_params[b:c], self.flat_grads[a:b], self.flat_grads[b:c]
 
-    def step(self, xs, teacher_feats, logits_s=None, logits_t=None, log=None):
-        """One pass; returns (hint_loss_sum, kd_loss) as 0-dim device tensors (no host sync)."""
+    def step(self, xs, teacher_feats, logits_s=None, logits_t=None, log=None, site_done=None):
+        """One pass; returns (hint_loss_sum, kd_loss) as 0-dim device tensors (no host sync).  `site_done(lo, hi)` is called
+        when the gradients flat_grads[lo:hi] of a site are final (its weight-gradient kernels are enqueued): the hook of the
+        data-parallel gradient exchange, which overlaps the transfer with the remaining sites."""
         L, st, code, n, lay = self.L, _stream(), self.code, self.N, self.layout
         H, W, Ho, Wo, k, d, p = self.H, self.W, self.Ho, self.Wo, self.k, self.d, self.p
         chk = _abi.check
@@ -192,8 +202,9 @@ class HotPathStep:
                 y_io, dy_io = self.y_cl, self.dy_cl
                 mark("relayout")
                 launches += 1
-            chk(L.kdcc_hint_loss(_ptr(y_io), _ptr(tf), None, 0, _ptr(dy_io), _ptr(self.hint_losses[i:]), ws, wsn,
-                                 n, co, Ho * Wo, self.io_layout, self.nc, code, 1.0 / self.acc_steps, st), "hint_loss")
+            chk(L.kdcc_hint_loss(_ptr(y_io), _ptr(tf), _ptr(self.hint_w[i]) if self.hint_w else None, 0, _ptr(dy_io),
+                                 _ptr(self.hint_losses[i:]), ws, wsn, n, co, Ho * Wo, self.io_layout,
+                                 1.0 if self.hint_w else self.nc, code, 1.0 / self.acc_steps, st), "hint_loss")
             mark("hint_loss")
             if rl:   # ... and its gradient arrives channels_last
                 chk(L.kdcc_layout_convert(_ptr(self.dy_cl), _ptr(self.dy), n, co, Ho * Wo, 1, code, st), "relayout")
@@ -206,6 +217,8 @@ class HotPathStep:
             chk(L.kdcc_dw_bwd(_ptr(x), _ptr(w_dw), _ptr(self.dmid), _ptr(self.dx) if self.need_dx[i] else None, _ptr(g_dw),
                               None, ws, wsn, n, H, W, ci, k, d, p, lay, code, st), "dw_bwd")
             mark("dw_bwd")
+            if site_done is not None:
+                site_done(self._views[i][0], self._views[i][2])
             if rl and self.need_dx[i]:   # the input gradient goes back channels_last
                 chk(L.kdcc_layout_convert(_ptr(self.dx), _ptr(self.dx_cl), n, ci, H * W, 0, code, st), "relayout")
                 mark("relayout")

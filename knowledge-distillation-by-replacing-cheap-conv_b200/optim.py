@@ -29,12 +29,19 @@ class RAdam(Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, buffer=[[None, None, None] for _ in range(10)])
         super().__init__(params, defaults)
         self._lp = {}
+        self._sources = {}
 
     def attach_lp_copy(self, param, lp_tensor):
         """`lp_tensor` (bf16, same numel, contiguous) is rewritten with the new value of `param` by every step."""
         if lp_tensor.dtype != torch.bfloat16 or lp_tensor.numel() != param.numel() or not lp_tensor.is_contiguous():
             raise _abi.KdccError("the low-precision copy must be a contiguous bf16 tensor of the parameter's size")
         self._lp[param] = lp_tensor
+
+    def attach_grad_sources(self, param, sources):
+        """Data-parallel form: `sources()` -> (view of source 0's copy of this parameter's gradient, floats between sources,
+        number of sources); the step then uses the mean of the copies (kdcc_radam_step_multi), i.e. the gradient all-reduce
+        is fused into the optimizer pass.  See kdcc.PeerGradBucket, which fills the copies over NVLink."""
+        self._sources[param] = sources
 
     def step_scalars(self, step, beta1, beta2):
         """(N_sma, step_size) of radam.py:65-84 (host float64, as there)."""
@@ -79,10 +86,16 @@ class RAdam(Optimizer):
                 cached = None
                 if lp is None:   # a bf16 copy some forward made of this master weight: refresh it in the same pass
                     lp = cached = lp_copy_of(p)
-                _abi.check(L.kdcc_radam_step(p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(), state['exp_avg_sq'].data_ptr(),
-                                             lp.data_ptr() if lp is not None else None, p.numel(), beta1, beta2, 1 - beta1, 1 - beta2, group['eps'],
-                                             -group['weight_decay'] * group['lr'], -size * group['lr'], mode,
-                                             torch.cuda.current_stream(p.device).cuda_stream), "kdcc_radam_step")
+                tail = (lp.data_ptr() if lp is not None else None, p.numel(), beta1, beta2, 1 - beta1, 1 - beta2, group['eps'],
+                        -group['weight_decay'] * group['lr'], -size * group['lr'], mode, torch.cuda.current_stream(p.device).cuda_stream)
+                src = self._sources.get(p)
+                if src is None:
+                    _abi.check(L.kdcc_radam_step(p.data_ptr(), g.data_ptr(), state['exp_avg'].data_ptr(), state['exp_avg_sq'].data_ptr(),
+                                                 *tail), "kdcc_radam_step")
+                else:
+                    g0, stride, n_src = src()
+                    _abi.check(L.kdcc_radam_step_multi(p.data_ptr(), g0.data_ptr(), int(stride), int(n_src), state['exp_avg'].data_ptr(),
+                                                       state['exp_avg_sq'].data_ptr(), *tail), "kdcc_radam_step_multi")
                 # the kernel wrote p through a raw pointer: move its version counter like an in-place op would, so autograd's
                 # saved-tensor checks and the weight-copy cache see the update
                 torch.autograd.graph.increment_version(p)

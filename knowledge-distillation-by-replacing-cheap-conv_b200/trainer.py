@@ -20,12 +20,17 @@ import torch.distributed as dist
 
 
 class GradBucket:
-    """Flat fp32 view of the trainable parameters' gradients: one all-reduce per optimizer step.
-    Rebuild it (`GradBucket(params)`) whenever prepare_train_epoch changes the trainable set."""
+    """Flat fp32 view of the trainable parameters' gradients: one exchange per optimizer step.
+    Rebuild it (`GradBucket(params)`) whenever prepare_train_epoch changes the trainable set.
+
+    `peer=True` (CUDA, world > 1, kdcc.optim.RAdam): the bucket lives in a symmetric buffer (kdcc.PeerGradBucket); every
+    parameter's gradient is pushed to the peers by copy engines the moment autograd has finished accumulating it, and the
+    optimizer averages the ranks' copies inside its fused pass -- no collective kernel on the step's critical path.
+    Otherwise: one NCCL (or gloo) all-reduce after the backward."""
 
     ALIGN = 32  # floats
 
-    def __init__(self, params):
+    def __init__(self, params, peer=False, group=None, optimizer=None, push_in_backward=True):
         self.params = [p for p in params if p.requires_grad]
         # every gradient starts on a 128-byte boundary of the bucket (32 floats): the fused optimizer and the GEMM
         # epilogues use 16-byte accesses, and a 19-element classifier bias must not misalign whatever follows it
@@ -34,11 +39,36 @@ class GradBucket:
             self.offsets.append(off)
             off += -(-p.numel() // self.ALIGN) * self.ALIGN
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.peer, self._hooks, self._pushed = None, [], False
+        if peer and self.params and dev.type == "cuda" and dist.is_available() and dist.is_initialized() and \
+                dist.get_world_size(group) > 1 and hasattr(optimizer, "attach_grad_sources"):
+            from .peer_reduce import PeerGradBucket
+            self.peer = PeerGradBucket(off, dev, group)
+            self.flat = self.peer.local()
+            for p, o in zip(self.params, self.offsets):
+                optimizer.attach_grad_sources(p, lambda o=o, n=p.numel(): (self.peer.sources()[0][o:o + n],) + self.peer.sources()[1:])
+                if push_in_backward:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(
+                        lambda prm, o=o, n=p.numel(): self._push(o, o + n)))
+        else:
+            self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self._point_grads()
+
+    def _point_grads(self):
         for p, o in zip(self.params, self.offsets):  # .grad become views into the bucket: no copies at step time
             p.grad = self.flat[o:o + p.numel()].view_as(p)
 
+    def _push(self, lo, hi):
+        self.peer.push(lo, hi)
+        self._pushed = True
+
     def zero(self):
+        """After the optimizer step: == optimizer.zero_grad() for the trainable set, keeps the flat views alive."""
+        if self.peer is not None:   # the next step fills the other parity of the symmetric buffer
+            self.peer.flip()
+            self.flat = self.peer.local()
+            self._point_grads()
+            self._pushed = False
         self.flat.zero_()
 
     def dense(self):
@@ -46,6 +76,12 @@ class GradBucket:
         return torch.cat([self.flat[o:o + p.numel()] for p, o in zip(self.params, self.offsets)]) if self.params else self.flat
 
     def all_reduce_mean(self, group=None):
+        """Make the rank-averaged gradient available to the optimizer step that follows."""
+        if self.peer is not None:
+            if not self._pushed:                 # nothing went out during the backward (hooks off, or gradient accumulation)
+                self.peer.push(0, self.peer.numel)
+            self.peer.finish()
+            return
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             world = dist.get_world_size(group)
             if dist.get_backend(group) == "nccl":
@@ -53,6 +89,11 @@ class GradBucket:
             else:  # gloo has no AVG
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
                 self.flat.div_(world)
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
 
 
 def _expect(criterion, value):
@@ -65,16 +106,23 @@ def _expect(criterion, value):
 class LayerwiseStep:
     """criterions = [supervised, kd, hint] as in train.py:48-50; `model` is a DepthwiseStudent."""
 
-    def __init__(self, model, criterions, optimizer, accumulation_steps=1, process_group=None, log_supervised=True):
+    def __init__(self, model, criterions, optimizer, accumulation_steps=1, process_group=None, log_supervised=True,
+                 peer_exchange=True):
         self.model, self.criterions, self.optimizer = model, criterions, optimizer
         self.accumulation_steps = int(accumulation_steps)
         self.group = process_group
         self.log_supervised = log_supervised
-        self.bucket = GradBucket(model.trainable_parameters())
+        self.peer_exchange = peer_exchange
+        self.bucket = None
+        self.rebuild_bucket()
         _expect(criterions[2], 1.0 / self.accumulation_steps)   # loss = sum(hint pairs) / accumulation_steps
 
     def rebuild_bucket(self):
-        self.bucket = GradBucket(self.model.trainable_parameters())
+        if self.bucket is not None:
+            self.bucket.close()
+        # gradients leave for the peers while the backward is still running only when every backward ends in a step
+        self.bucket = GradBucket(self.model.trainable_parameters(), peer=self.peer_exchange, group=self.group,
+                                 optimizer=self.optimizer, push_in_backward=self.accumulation_steps == 1)
 
     def __call__(self, data, target, batch_idx):
         acc = self.accumulation_steps

@@ -35,13 +35,16 @@ def test_kdcc_arm_fails_loudly_without_a_gpu():
     assert "cuda" in (r.stderr + r.stdout).lower()
 
 
-def test_tensor_issue_floor_model():
-    """roofline.tensor_issue_floor: DESIGN.md 4.0's MMA cost model applied to the default workload."""
+def test_smem_floor_model():
+    """roofline.smem_floor: DESIGN.md 4.0's shared-memory byte model applied to the default workload."""
     sys.path.insert(0, ROOT)
     import bench
     plan = bench.plan_51m()
+    need_dx = [False] + [True] * (len(plan) - 1)
     planes = 4 * sum(ci for ci, _ in plan)
-    f = bench.tensor_issue_floor(plan, 4, (9, 5, 20), "nchw", 128, 3.25, 1900.0)
-    assert abs(f["ms"] - planes * (90 * 59 + 72 * 74) / 148 / 1.9e6) < 1e-3 and 0 < f["frac"] < 1
-    assert bench.tensor_issue_floor(plan, 4, (9, 5, 20), "nhwc", 128, 3.25, 1900.0) is None
-    assert bench.tensor_issue_floor(plan, 4, (9, 5, 20), "nchw", 128, 3.25, None) is None
+    f = bench.smem_floor(plan, 4, (9, 5, 20), "nchw", 128, need_dx, 3.15, 1900.0)
+    want = ((planes - 4 * plan[0][0]) * 618 * 1024 + planes * 648 * 1024) / 128 / 148 / 1.9e6
+    assert abs(f["ms"] - want) < 1e-3 and 0 < f["frac"] < 1
+    assert bench.smem_floor(plan, 4, (9, 5, 20), "nhwc", 128, need_dx, 3.15, 1900.0) is None
+    assert bench.smem_floor(plan, 4, (9, 5, 20), "nchw", 128, need_dx, 3.15, None) is None
+    assert bench.smem_floor(plan, 4, (3, 1, 1), "nchw", 128, need_dx, 3.15, 1900.0) is None

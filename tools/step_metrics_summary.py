@@ -27,17 +27,20 @@ fam_of = {"cast_f32_to_bf16_kernel": "cast_w", "hint_loss_kernel": "hint_loss", 
           "kd_loss_kernel": "kd_loss", "reduce_splits_kernel": "pw_bwd_dw", "dw_tc_wgrad2_kernel": "dw_bwd(dW)",
           "dw_tc_wgrad2_reduce_kernel": "dw_bwd(dW)"}
 order = list(launch.values())
-conv_seen = gemm_seen = 0
+# per site (kdcc.hotpath.HotPathStep.step): conv (fwd), GEMM fwd, hint, GEMM dW (+ split reduce), GEMM dX, [conv (dX) -- absent
+# when the site needs no input gradient], weight-gradient kernel (+ reduce).  A conv that directly follows a GEMM is the dX conv.
+gemm_seen = 0
+prev = ""
 for e in order:
     n = e["name"]
-    if n == "dw_tc_conv2_kernel":  # per site: forward conv, ..., input-gradient conv
-        e["fam"] = "dw_fwd" if conv_seen % 2 == 0 else "dw_bwd(dX)"
-        conv_seen += 1
+    if n == "dw_tc_conv2_kernel":
+        e["fam"] = "dw_bwd(dX)" if prev == "pw_gemm_sm100_kernel" else "dw_fwd"
     elif n == "pw_gemm_sm100_kernel":
         e["fam"] = ("pw_fwd", "pw_bwd_dw", "pw_bwd_dx")[gemm_seen % 3]
         gemm_seen += 1
     else:
         e["fam"] = fam_of.get(n, n)
+    prev = n
 
 def to_bytes(e, key):
     v, u = e.get(key, 0.0), e.get("units", {}).get(key, "byte")
@@ -80,5 +83,11 @@ for k, f in fams.items():
 traffic["dw_bwd"] = {"dram_bytes_per_step": traffic["dw_bwd(dX)"]["dram_bytes_per_step"] + traffic["dw_bwd(dW)"]["dram_bytes_per_step"],
                      "launches": traffic["dw_bwd(dX)"]["launches"] + traffic["dw_bwd(dW)"]["launches"],
                      "ncu_us": round(traffic["dw_bwd(dX)"]["ncu_us"] + traffic["dw_bwd(dW)"]["ncu_us"], 1)}
-json.dump({"source": src, "config": "bench.py default: batch 4, 51M plan, k9d5p20, nchw bf16", "families": traffic}, open(js, "w"), indent=1)
+import subprocess
+try:
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or None
+except Exception:
+    commit = None
+json.dump({"source": src, "config": "bench.py default: batch 4, 51M plan, k9d5p20, nchw bf16; no input gradient for the first site",
+           "summarised_at_commit": commit, "families": traffic}, open(js, "w"), indent=1)
 print(open(txt).read())
