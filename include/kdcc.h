@@ -33,7 +33,11 @@ extern "C" {
 #define KDCC_VERSION 104 /* round 1: layout-aware depthwise/pointwise, confusion matrix, multi-teacher KD, TTA stitch, RAdam */
 
 enum { KDCC_F32 = 0, KDCC_BF16 = 1 };
-enum { KDCC_LAYOUT_NHWC = 0, KDCC_LAYOUT_NCHW = 1 };
+enum { KDCC_LAYOUT_NHWC = 0, KDCC_LAYOUT_NCHW = 1,
+       /* pointwise entry points only: the block-INTERNAL tensor (depthwise output `x`, its gradient `dx`) is channel planes
+        * (NCHW), the block-EXTERNAL one (`y`, `dy`) is channels_last -- a block whose depthwise ran on planes inside a
+        * channels_last trunk hands its result over without a separate re-layout pass */
+       KDCC_LAYOUT_PLANES_TO_NHWC = 2 };
 
 enum {
   KDCC_OK = 0,

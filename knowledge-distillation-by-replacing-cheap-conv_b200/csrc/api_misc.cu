@@ -48,7 +48,7 @@ KDCC_API const char *kdcc_dispatch_name(int op, int N, int H, int W, int C, int 
     case 2: case 3: case 4: {
       static const char *names[3] = {"pw_gemm_sm100_fwd", "pw_gemm_sm100_dx", "pw_gemm_sm100_dw"};
       if (bf16 && pw_sm100_supported(M, C, Cout, N, layout)) return names[op - 2];
-      return nchw ? "unsupported" : "pw_simt";
+      return layout != KDCC_LAYOUT_NHWC ? "unsupported" : "pw_simt";
     }
     default: return "?";
   }

@@ -17,9 +17,9 @@ static bool use_sm100(long M, int K, int Nc, int batch, int layout, int dtype) {
 static int check(long M, int K, int Nc, int batch, int layout, int dtype) {
   if (M < 0 || K <= 0 || Nc <= 0) return KDCC_EINVAL;
   if (dtype != KDCC_F32 && dtype != KDCC_BF16) return KDCC_EINVAL;
-  if (layout != KDCC_LAYOUT_NHWC && layout != KDCC_LAYOUT_NCHW) return KDCC_EINVAL;
+  if (layout != KDCC_LAYOUT_NHWC && layout != KDCC_LAYOUT_NCHW && layout != KDCC_LAYOUT_PLANES_TO_NHWC) return KDCC_EINVAL;
   if (M >= (1L << 31)) return KDCC_ESHAPE;
-  if (layout == KDCC_LAYOUT_NCHW) {
+  if (layout != KDCC_LAYOUT_NHWC) {
     if (batch <= 0 && M > 0) return KDCC_EINVAL;
     // the NCHW form exists on the tensor-core path only
     if (M > 0 && (dtype != KDCC_BF16 || !pw_sm100_supported(M, K, Nc, batch, layout))) return KDCC_ESHAPE;
@@ -40,7 +40,7 @@ static int pw_fwd_impl(const void *x, const void *w, const float *scale, const f
       return KDCC_EALIGN;
     return pw_sm100_fwd(x, w, scale, shift, residual, relu, y_raw, y_act, M, K, Nc, batch, layout, st);
   }
-  if (layout == KDCC_LAYOUT_NCHW) return KDCC_ESHAPE;
+  if (layout != KDCC_LAYOUT_NHWC) return KDCC_ESHAPE;
   SimtGemm g{};
   g.I = (int)M; g.J = Nc; g.R = K;
   g.sai = K; g.sar = 1; g.sbj = K; g.sbr = 1; g.splits = 1;
@@ -81,7 +81,7 @@ KDCC_API int kdcc_pw_bwd_dx(const void *dy, const void *w, void *dx, void *works
     if (!aligned16(dy) || !aligned16(w) || !aligned16(dx)) return KDCC_EALIGN;
     return pw_sm100_bwd_dx(dy, w, dx, M, K, Nc, batch, layout, st);
   }
-  if (layout == KDCC_LAYOUT_NCHW) return KDCC_ESHAPE;
+  if (layout != KDCC_LAYOUT_NHWC) return KDCC_ESHAPE;
   // dx[m][k] = sum_n dy[m][n] w[n][k]
   SimtGemm g{};
   g.I = (int)M; g.J = K; g.R = Nc;
@@ -104,7 +104,7 @@ KDCC_API int kdcc_pw_bwd_dw(const void *dy, const void *x, float *dw, void *work
     if (!aligned16(dy) || !aligned16(x) || !aligned16(dw) || !aligned16(part)) return KDCC_EALIGN;
     return pw_sm100_bwd_dw(dy, x, dw, part, M, K, Nc, batch, layout, st);
   }
-  if (layout == KDCC_LAYOUT_NCHW) return KDCC_ESHAPE;
+  if (layout != KDCC_LAYOUT_NHWC) return KDCC_ESHAPE;
   // dw[n][k] = sum_m dy[m][n] x[m][k]
   SimtGemm g{};
   g.I = Nc; g.J = K; g.R = (int)M;

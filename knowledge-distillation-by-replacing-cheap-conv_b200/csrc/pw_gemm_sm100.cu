@@ -439,6 +439,7 @@ bool pw_sm100_supported(long M, int K, int Nc, int batch, int layout) {
   // 16-byte global strides for TMA and 16-byte epilogue stores
   if (M <= 0 || M >= (1L << 31) || K % 8 != 0) return false;
   if (layout == KDCC_LAYOUT_NCHW) return batch > 0 && M % batch == 0 && (M / batch) % 8 == 0;
+  if (layout == KDCC_LAYOUT_PLANES_TO_NHWC) return batch > 0 && M % batch == 0 && (M / batch) % 8 == 0 && Nc % 8 == 0;
   return Nc % 8 == 0;
 }
 
@@ -454,8 +455,14 @@ int pw_sm100_fwd(const void *x, const void *w, const float *scale, const float *
     p.I = (int)M; p.J = Nc; p.R = K; p.batch = 1;
     return gemm_dispatch_bj<false, false>(x, w, p, st);
   }
-  // NCHW: y_b[n][pix] = sum_k w[n][k] x_b[k][pix] : A = w (shared, K-major), B = x_b (pixel-contiguous, MN-major)
   const int P = (int)(M / batch);
+  if (layout == KDCC_LAYOUT_PLANES_TO_NHWC) {
+    // x planes, y channels_last: y_b[pix][n] = sum_k x_b[k][pix] w[n][k] : A = x_b (pixel-contiguous: MN-major), B = w (K-major)
+    p.I = P; p.J = Nc; p.R = K; p.batch = batch; p.a_batched = 1; p.b_batched = 0;
+    p.out_batch_stride = (long)P * Nc;
+    return gemm_dispatch_bj<true, false>(x, w, p, st);
+  }
+  // NCHW: y_b[n][pix] = sum_k w[n][k] x_b[k][pix] : A = w (shared, K-major), B = x_b (pixel-contiguous, MN-major)
   p.I = Nc; p.J = P; p.R = K; p.batch = batch; p.a_batched = 0; p.b_batched = 1;
   p.out_batch_stride = (long)Nc * P; p.affine_rows = 1;
   return gemm_dispatch_bj<false, true>(w, x, p, st);
@@ -474,6 +481,8 @@ int pw_sm100_bwd_dx(const void *dy, const void *w, void *dx, long M, int K, int 
   const int P = (int)(M / batch);
   p.I = K; p.J = P; p.R = Nc; p.batch = batch; p.a_batched = 0; p.b_batched = 1;
   p.out_batch_stride = (long)K * P;
+  // dy channels_last, dx planes: B = dy_b [pix][n] is r-contiguous (K-major)
+  if (layout == KDCC_LAYOUT_PLANES_TO_NHWC) return gemm_dispatch_bj<true, false>(w, dy, p, st);
   return gemm_dispatch_bj<true, true>(w, dy, p, st);
 }
 
@@ -517,7 +526,9 @@ int pw_sm100_bwd_dw(const void *dy, const void *x, float *dw, float *part, long 
     p.splits = dw_splits_for((long)batch * ceil_div(P, GEMM_BR), K, Nc);
     if (p.splits > pw_sm100_dw_splits(M, K, Nc)) return KDCC_EWORKSPACE;  // the caller's workspace is sized by that bound
     p.out_f32 = p.splits == 1 ? dw : part;
-    rc = gemm_dispatch_bj<false, false>(dy, x, p, st);
+    // dy channels_last [pix][n] (n-contiguous: MN-major A), x planes [k][pix] (K-major B)
+    if (layout == KDCC_LAYOUT_PLANES_TO_NHWC) rc = gemm_dispatch_bj<true, false>(dy, x, p, st);
+    else rc = gemm_dispatch_bj<false, false>(dy, x, p, st);
   }
   if (rc || p.splits == 1) return rc;
   const long count = (long)Nc * K;  // multiple of 4 because K % 8 == 0

@@ -223,6 +223,7 @@ class _DepthwiseConv(torch.autograd.Function):
         ctx.save_for_backward(x, w)
         ctx.geom = (k, dil, pad, bias is not None, weight.shape, layout)
         ctx.in_cl = in_cl
+        ctx.wdtype = weight.dtype   # fp32 master weights normally; a model cast wholesale to bf16 gets its gradients in bf16
         return y
 
     @staticmethod
@@ -243,7 +244,7 @@ class _DepthwiseConv(torch.autograd.Function):
                                  N, H, W, C, k, dil, pad, layout, code, _stream()), "kdcc_dw_bwd")
         if need_dx and ctx.in_cl:
             dx = _convert(dx, False)   # the gradient goes back in the layout the input came in
-        return dx, (dw.reshape(wshape) if need_dw else None), db, None, None, None
+        return dx, (dw.reshape(wshape).to(ctx.wdtype) if need_dw else None), db, None, None, None
 
 
 def depthwise_conv(x, weight, bias, kernel_size, dilation, padding):
@@ -266,9 +267,12 @@ class _PointwiseConv(torch.autograd.Function):
         layout = _abi.NHWC
         if _is_plain_nchw(x) and _supported(2, N, H, W, K, Co, 1, 1, 0, _abi.NCHW, code):
             layout = _abi.NCHW
-        x = _format(x, layout)
+            # planes in, channels_last out: the GEMM writes the caller's layout itself (no re-layout pass for y and dy)
+            if out_channels_last and Co % 8 == 0 and _supported(2, N, H, W, K, Co, 1, 1, 0, _abi.PLANES_TO_NHWC, code):
+                layout = _abi.PLANES_TO_NHWC
+        x = _format(x, _abi.NCHW if layout == _abi.PLANES_TO_NHWC else layout)
         w = lp_weight(weight, x.dtype).reshape(Co, K)
-        y = _empty_like_layout(N, Co, H, W, x, layout)
+        y = _empty_like_layout(N, Co, H, W, x, _abi.NHWC if layout == _abi.PLANES_TO_NHWC else layout)
         fused = scale is not None or shift is not None or relu
         eff_shift = shift
         if bias is not None and not fused:
@@ -279,7 +283,7 @@ class _PointwiseConv(torch.autograd.Function):
         if residual is not None:
             if residual.shape != y.shape:
                 raise _abi.KdccError("residual %s does not match the output %s" % (tuple(residual.shape), tuple(y.shape)))
-            res = _format(residual.detach().to(x.dtype), layout)
+            res = _format(residual.detach().to(x.dtype), _abi.NHWC if layout == _abi.PLANES_TO_NHWC else layout)
             _abi.check(_abi.lib().kdcc_pw_fwd_residual(_ptr(x), _ptr(w), _ptr(scale), _ptr(eff_shift), _ptr(res), int(bool(relu)),
                                                        None, _ptr(y), M, K, Co, N, layout, code, _stream()), "kdcc_pw_fwd_residual")
         else:
@@ -292,6 +296,7 @@ class _PointwiseConv(torch.autograd.Function):
             ctx.mark_non_differentiable(y)  # inference-only epilogue (eval-mode BN fold)
         ctx.save_for_backward(x, w)
         ctx.meta = (bias is not None, weight.shape, layout)
+        ctx.wdtype = weight.dtype
         ctx.has_residual = residual is not None
         return y
 
@@ -303,20 +308,21 @@ class _PointwiseConv(torch.autograd.Function):
         N, K, H, W = x.shape
         Co = w.shape[0]
         M = N * H * W
-        dy = _format(dy, layout)
+        mixed = layout == _abi.PLANES_TO_NHWC
+        dy = _format(dy, _abi.NHWC if mixed else layout)
         L = _abi.lib()
         code = _dtype_code(x)
         st = _stream()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _empty_like_layout(N, K, H, W, x, layout)
+            dx = _empty_like_layout(N, K, H, W, x, _abi.NCHW if mixed else layout)
             _abi.check(L.kdcc_pw_bwd_dx(_ptr(dy), _ptr(w), _ptr(dx), None, 0, M, K, Co, N, layout, code, st), "kdcc_pw_bwd_dx")
         if ctx.needs_input_grad[1]:
             dw = torch.empty((Co, K), dtype=torch.float32, device=x.device)
             ws = _workspace(L.kdcc_pw_bwd_workspace_bytes(1, M, K, Co, code), x.device)
             _abi.check(L.kdcc_pw_bwd_dw(_ptr(dy), _ptr(x), _ptr(dw), _ptr(ws), ws.numel(), M, K, Co, N, layout, code, st),
                        "kdcc_pw_bwd_dw")
-            dw = dw.reshape(wshape)
+            dw = dw.reshape(wshape).to(ctx.wdtype)
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty((Co,), dtype=torch.float32, device=x.device)
             dyr = _nhwc(dy)  # column sums are taken over the pixel-major view

@@ -23,14 +23,30 @@ PLAN_CIFAR_RESNET44 = [(64, 64)] * 8                                           #
 
 
 class EventLog:
-    """CUDA-event timeline on the launching stream: one event after every kernel call."""
+    """CUDA-event timeline on the launching stream: one event after every kernel call.
 
-    def __init__(self, external=False):
+    `only`: record just these families (an event before and one after each of their calls) and nothing else.  An event
+    record between two kernels ends the programmatic-dependent-launch overlap of their tail and prologue, so a full
+    timeline costs the step ~4 %; bench.py therefore brackets only the dominant family inside its timed region and takes
+    the complete per-kernel table from a separate instrumented pass."""
+
+    def __init__(self, external=False, only=None):
         # external=True: events that may be recorded inside a CUDA-graph capture (they become event-record nodes and
         # are re-recorded by every replay, so the log then holds the timeline of the LAST replay)
         self.names, self.events, self.external = [], [], external
+        self.only = set(only) if only else None
+
+    def pre(self, name):
+        """Start-of-call mark; needed only when the log is selective (otherwise the previous call's mark is the start)."""
+        if self.only is not None and name in self.only:
+            self._record("begin")
 
     def mark(self, name):
+        if self.only is not None and name not in self.only:
+            return
+        self._record(name)
+
+    def _record(self, name):
         ev = torch.cuda.Event(enable_timing=True, external=True) if self.external else torch.cuda.Event(enable_timing=True)
         ev.record(torch.cuda.current_stream())
         self.names.append(name)
@@ -49,7 +65,8 @@ class EventLog:
 class HotPathStep:
     def __init__(self, plan, batch, height, width, kernel_size=9, dilation=5, padding=20, dtype=torch.bfloat16,
                  device="cuda", logits_shape=None, kd_temperature=1.0, hint_num_classes=1000.0,
-                 accumulation_steps=1, kd_grad=False, need_dx=True, seed=0, layout="nchw", hint_weighted=False):
+                 accumulation_steps=1, kd_grad=False, need_dx=True, seed=0, layout="nchw", hint_weighted=False,
+                 order="reference"):
         self.plan = list(plan)
         self.N, self.H, self.W = batch, height, width
         self.k, self.d, self.p = kernel_size, dilation, padding
@@ -106,8 +123,18 @@ class HotPathStep:
         self.y = e(omax, self.Ho, self.Wo)
         self.dy = e(omax, self.Ho, self.Wo)
         if self.relayout:  # channel-plane copies of what arrives / leaves channels_last
-            self.x_planes, self.y_cl, self.dy_cl = e(cmax, height, width), e(omax, self.Ho, self.Wo), e(omax, self.Ho, self.Wo)
+            self.x_planes = e(cmax, height, width)
             self.dx_cl = e(cmax, height, width) if any(self.need_dx) else None
+        # order "reference": forward of every site, the hint losses, then the backward in reverse site order -- what
+        # `model(data)` ... `loss.backward()` does -- so every site keeps its depthwise output, block output and gradient
+        # until its backward ("interleaved": forward + loss + backward site by site over shared scratch; 5 % slower)
+        self.order = order
+        if order == "reference":
+            es = (lambda c, h, w: torch.empty((n, c, h, w), dtype=dtype, device=self.device))
+            self.mid_s = [es(ci, self.Ho, self.Wo) for ci, _ in self.plan]
+            self.y_s = [es(co, self.Ho, self.Wo) for _, co in self.plan]
+            self.dy_s = [es(co, self.Ho, self.Wo) for _, co in self.plan]
+            self.xp_s = [es(ci, height, width) for ci, _ in self.plan] if self.relayout else None
         # bf16 copy of the WHOLE flat parameter bucket, refreshed by one cast launch per step (the pointwise GEMMs read
         # their weights from it; one launch instead of one per site)
         self.flat_lp = torch.empty(total, dtype=dtype, device=self.device)
@@ -172,48 +199,66 @@ class HotPathStep:
         chk = _abi.check
         ws, wsn = _ptr(self.ws), self.ws.numel()
         mark = log.mark if log is not None else (lambda name: None)
+        pre = log.pre if log is not None else (lambda name: None)
         launches = 0
         mark("begin")
         if code == _abi.BF16 and not self.lp_maintained:
             chk(L.kdcc_cast_f32_to_bf16(_ptr(self.flat_params), _ptr(self.flat_lp), self.flat_params.numel(), st), "cast")
             mark("cast_w")
             launches += 1
-        for i, (ci, co) in enumerate(self.plan):
+        rl = self.relayout
+        play = _abi.PLANES_TO_NHWC if rl else lay      # channels_last callers: the GEMMs read / write y and dy channels_last
+        M = n * Ho * Wo
+        per_site = self.order == "reference"
+
+        def buffers(i):
+            return (self.mid_s[i], self.y_s[i], self.dy_s[i], self.xp_s[i] if rl else None) if per_site else \
+                   (self.mid, self.y, self.dy, self.x_planes if rl else None)
+
+        def weights(i):
             w_dw, w_pw, g_dw, g_pw = self._site_weights(i)
-            x, tf = xs[i], teacher_feats[i]
-            M = n * Ho * Wo
-            w_lp = w_pw
-            if code == _abi.BF16:
-                a_, b_, c_ = self._views[i]
-                w_lp = self.flat_lp[b_:c_]
-            rl = self.relayout
+            w_lp = self.flat_lp[self._views[i][1]:self._views[i][2]] if code == _abi.BF16 else w_pw
+            return w_dw, w_lp, g_dw, g_pw
+
+        def forward(i):
+            nonlocal launches
+            ci, co = self.plan[i]
+            w_dw, w_lp, _, _ = weights(i)
+            mid, y, dy, xp = buffers(i)
+            x = xs[i]
             if rl:   # channels_last input -> channel planes
-                chk(L.kdcc_layout_convert(_ptr(x), _ptr(self.x_planes), n, ci, H * W, 1, code, st), "relayout")
-                x = self.x_planes
+                chk(L.kdcc_layout_convert(_ptr(x), _ptr(xp), n, ci, H * W, 1, code, st), "relayout")
+                x = xp
                 mark("relayout")
                 launches += 1
-            chk(L.kdcc_dw_fwd(_ptr(x), _ptr(w_dw), None, _ptr(self.mid), n, H, W, ci, k, d, p, lay, code, st), "dw_fwd")
+            pre("dw_fwd")
+            chk(L.kdcc_dw_fwd(_ptr(x), _ptr(w_dw), None, _ptr(mid), n, H, W, ci, k, d, p, lay, code, st), "dw_fwd")
             mark("dw_fwd")
-            chk(L.kdcc_pw_fwd(_ptr(self.mid), _ptr(w_lp), None, None, 0, _ptr(self.y), None, M, ci, co, n, lay, code, st), "pw_fwd")
+            chk(L.kdcc_pw_fwd(_ptr(mid), _ptr(w_lp), None, None, 0, _ptr(y), None, M, ci, co, n, play, code, st), "pw_fwd")
             mark("pw_fwd")
-            y_io, dy_io = self.y, self.dy
-            if rl:   # the block's output leaves channels_last (the hint is taken against a channels_last teacher feature)
-                chk(L.kdcc_layout_convert(_ptr(self.y), _ptr(self.y_cl), n, co, Ho * Wo, 0, code, st), "relayout")
-                y_io, dy_io = self.y_cl, self.dy_cl
-                mark("relayout")
-                launches += 1
-            chk(L.kdcc_hint_loss(_ptr(y_io), _ptr(tf), _ptr(self.hint_w[i]) if self.hint_w else None, 0, _ptr(dy_io),
+            launches += 2
+
+        def hint(i):
+            nonlocal launches
+            ci, co = self.plan[i]
+            mid, y, dy, xp = buffers(i)
+            chk(L.kdcc_hint_loss(_ptr(y), _ptr(teacher_feats[i]), _ptr(self.hint_w[i]) if self.hint_w else None, 0, _ptr(dy),
                                  _ptr(self.hint_losses[i:]), ws, wsn, n, co, Ho * Wo, self.io_layout,
                                  1.0 if self.hint_w else self.nc, code, 1.0 / self.acc_steps, st), "hint_loss")
             mark("hint_loss")
-            if rl:   # ... and its gradient arrives channels_last
-                chk(L.kdcc_layout_convert(_ptr(self.dy_cl), _ptr(self.dy), n, co, Ho * Wo, 1, code, st), "relayout")
-                mark("relayout")
-                launches += 1
-            chk(L.kdcc_pw_bwd_dw(_ptr(self.dy), _ptr(self.mid), _ptr(g_pw), ws, wsn, M, ci, co, n, lay, code, st), "pw_bwd_dw")
+            launches += 2   # pass + finalize
+
+        def backward(i):
+            nonlocal launches
+            ci, co = self.plan[i]
+            w_dw, w_lp, g_dw, g_pw = weights(i)
+            mid, y, dy, xp = buffers(i)
+            x = xp if rl else xs[i]
+            chk(L.kdcc_pw_bwd_dw(_ptr(dy), _ptr(mid), _ptr(g_pw), ws, wsn, M, ci, co, n, play, code, st), "pw_bwd_dw")
             mark("pw_bwd_dw")
-            chk(L.kdcc_pw_bwd_dx(_ptr(self.dy), _ptr(w_lp), _ptr(self.dmid), None, 0, M, ci, co, n, lay, code, st), "pw_bwd_dx")
+            chk(L.kdcc_pw_bwd_dx(_ptr(dy), _ptr(w_lp), _ptr(self.dmid), None, 0, M, ci, co, n, play, code, st), "pw_bwd_dx")
             mark("pw_bwd_dx")
+            pre("dw_bwd")
             chk(L.kdcc_dw_bwd(_ptr(x), _ptr(w_dw), _ptr(self.dmid), _ptr(self.dx) if self.need_dx[i] else None, _ptr(g_dw),
                               None, ws, wsn, n, H, W, ci, k, d, p, lay, code, st), "dw_bwd")
             mark("dw_bwd")
@@ -223,9 +268,24 @@ class HotPathStep:
                 chk(L.kdcc_layout_convert(_ptr(self.dx), _ptr(self.dx_cl), n, ci, H * W, 0, code, st), "relayout")
                 mark("relayout")
                 launches += 1
-            # dw_fwd 1, pw_fwd 1, hint 2 (pass + finalize), pw_dw 2 (gemm + split reduce), pw_dx 1,
-            # dw_bwd: wgrad 1 + reduce 1 (+ dx conv 1)
-            launches += 1 + 1 + 2 + 2 + 1 + (3 if self.need_dx[i] else 2)
+            # pw_dw 2 (gemm + split reduce), pw_dx 1, dw_bwd: wgrad 1 + reduce 1 (+ dx conv 1)
+            launches += 2 + 1 + (3 if self.need_dx[i] else 2)
+
+        sites = range(len(self.plan))
+        if per_site:
+            # the reference loop's order (trainer/layerwise_trainer.py:223-235): the student's forward pass visits every
+            # block, the hint criterion is evaluated over the hooked pairs, then loss.backward() walks the blocks in reverse
+            for i in sites:
+                forward(i)
+            for i in sites:
+                hint(i)
+            for i in reversed(sites):
+                backward(i)
+        else:
+            for i in sites:
+                forward(i)
+                hint(i)
+                backward(i)
         if logits_s is not None:
             N_, C_ = logits_s.shape[0], logits_s.shape[1]
             HW = logits_s.numel() // (N_ * C_)
@@ -264,8 +324,8 @@ class HotPathStep:
             out["pw_bwd_dx"] += flops
             out["pw_bwd_dw"] += flops
             out["hint_loss"] += 3 * n * P_out * co * es
-            if self.relayout:   # x in, y out, dy in (read + write each), dx out where it exists
-                out["relayout"] += 2 * es * n * (P_in * ci * (2 if self.need_dx[i] else 1) + 2 * P_out * co)
+            if self.relayout:   # x in (read + write), dx out where it exists; y and dy are handled inside the GEMMs
+                out["relayout"] += 2 * es * n * P_in * ci * (2 if self.need_dx[i] else 1)
         if self.logits_shape:
             numel = 1
             for s_ in self.logits_shape:

@@ -248,3 +248,28 @@ def test_channels_last_block_runs_on_the_tensor_core_path_and_returns_channels_l
     for name, mine, ref in (("y", host(y), ry), ("dx", host(xt.grad), rdx), ("dw_dw", host(blk.separable_conv.weight.grad), rdwd),
                             ("dw_pw", host(blk.pointwise_conv.weight.grad), rdwp)):
         assert relerr(mine, ref) < TOL[dtype], name
+
+
+@pytest.mark.parametrize("geom", [(2, 64, 128, 16, 24), (1, 512, 512, 128, 128), (3, 256, 72, 12, 20), (2, 4096, 256, 16, 16)])
+def test_pointwise_planes_in_channels_last_out(kdcc, geom):
+    """KDCC_LAYOUT_PLANES_TO_NHWC: the pointwise GEMMs take the block-internal tensor as channel planes and read / write the
+    block-external one channels_last (forward, dX, dW) -- no re-layout pass for y and dy inside a channels_last trunk."""
+    from oracle import oracle as orc
+    N, K, Co, H, W = geom
+    dtype = torch.bfloat16
+    rs = np.random.RandomState(K + Co + H)
+    x = q(rs.standard_normal((N, K, H, W)).astype(np.float32), dtype)
+    w = q((rs.uniform(-1, 1, (Co, K, 1, 1)) / np.sqrt(K)).astype(np.float32), dtype)
+    dy = q(rs.standard_normal((N, Co, H, W)).astype(np.float32), dtype)
+    xt = torch.from_numpy(x).cuda().to(dtype).requires_grad_(True)                       # plain NCHW: planes
+    wt = torch.from_numpy(w).cuda().requires_grad_(True)
+    assert kdcc._abi.dispatch_name(2, N, H, W, K, Co, 1, 1, 0, kdcc._abi.PLANES_TO_NHWC, kdcc._abi.BF16) == "pw_gemm_sm100_fwd"
+    y = kdcc.functional.pointwise_conv(xt, wt, out_channels_last=True)
+    assert y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous()
+    y.backward(torch.from_numpy(dy).cuda().to(dtype).contiguous(memory_format=torch.channels_last))
+    assert xt.grad.is_contiguous()
+    ry = orc.pw_fwd(x, w)
+    rdx, rdw, _ = orc.pw_bwd(x, w, dy)
+    assert relerr(host(y), ry) < TOL[dtype]
+    assert relerr(host(xt.grad), rdx) < TOL[dtype]
+    assert relerr(host(wt.grad), rdw) < TOL[dtype]

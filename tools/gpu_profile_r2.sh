@@ -3,8 +3,9 @@
 #   1. launch list (duration of every launch) of a short bench run                      -> gpurun_out/r2_launches.csv
 #   2. DRAM / L2 / tensor counters of every kdcc kernel of one timed step                -> gpurun_out/r2_step_metrics.csv
 #   3. --set full + source of the dominant kernels at the largest site (4096 channels)   -> gpurun_out/r2_prof_*.ncu-rep
-# Per step the filter K matches 91 launches (site 0: 9, sites 1-8: 10 each, KD loss 2); before the timed step of run B there is
-# the initial weight cast and 3 warm-up steps: 1 + 3 * 91 = 274.
+# bench.py brackets its timed region with cudaProfilerStart/Stop: with --profile-from-start off ncu sees exactly the timed
+# step(s), whatever ran before.  Conv launches of one step in order: site 0 forward, then forward + dX of sites 1-8 (the 4096-
+# channel sites are the last three: conv index 11..16, weight-gradient index 6..8, GEMM index 18..26).
 mkdir -p gpurun_out
 K='dw_tc|pw_gemm|loss|cast_f32|reduce_splits|wgrad2_reduce'
 M='gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,sm__cycles_elapsed.max,launch__registers_per_thread,launch__shared_mem_per_block_dynamic,launch__grid_size,launch__block_size'
@@ -12,16 +13,16 @@ X="--no-cpu-baseline --no-gpu-baseline --no-extras --e2e-steps 0"
 A="--steps 3 --warmup 3 $X"
 B="--steps 1 --warmup 3 $X"
 python bench.py $A > gpurun_out/r2_plain_a.json 2> gpurun_out/r2_plain_a.err &&
-timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2_launches.csv python bench.py $A > gpurun_out/r2_ncu_launches.out 2>&1
+timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/r2_launches.csv python bench.py $A > gpurun_out/r2_ncu_launches.out 2>&1
 echo "launch list rc=$?"
 python bench.py $B > gpurun_out/r2_plain_b.json 2> gpurun_out/r2_plain_b.err || exit 1
-timeout -s KILL 600 ncu --metrics $M --clock-control none -k regex:"$K" -s 274 -c 91 --csv --log-file gpurun_out/r2_step_metrics.csv python bench.py $B > gpurun_out/r2_ncu_step.out 2>&1
+timeout -s KILL 600 ncu --metrics $M --clock-control none --profile-from-start off -k regex:"$K" --csv --log-file gpurun_out/r2_step_metrics.csv python bench.py $B > gpurun_out/r2_ncu_step.out 2>&1
 echo "step metrics rc=$?"
-timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:dw_tc_conv2 -s 66 -c 2 -o gpurun_out/r2_prof_conv2 -f python bench.py $B > gpurun_out/r2_ncu_full1.out 2>&1
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:dw_tc_conv2 -s 11 -c 2 -o gpurun_out/r2_prof_conv2 -f python bench.py $B > gpurun_out/r2_ncu_full1.out 2>&1
 echo "full conv2 rc=$?"
-timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:dw_tc_wgrad2_kernel -s 35 -c 1 -o gpurun_out/r2_prof_wgrad2 -f python bench.py $B > gpurun_out/r2_ncu_full2.out 2>&1
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:dw_tc_wgrad2_kernel -s 6 -c 1 -o gpurun_out/r2_prof_wgrad2 -f python bench.py $B > gpurun_out/r2_ncu_full2.out 2>&1
 echo "full wgrad2 rc=$?"
-timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:pw_gemm -s 105 -c 3 -o gpurun_out/r2_prof_gemm -f python bench.py $B > gpurun_out/r2_ncu_full3.out 2>&1
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:pw_gemm -s 18 -c 3 -o gpurun_out/r2_prof_gemm -f python bench.py $B > gpurun_out/r2_ncu_full3.out 2>&1
 echo "full gemm rc=$?"
 python tools/step_metrics_summary.py gpurun_out/r2_step_metrics.csv gpurun_out/r2_step_metrics.txt gpurun_out/r2_traffic.json | tail -20
 for f in conv2 wgrad2 gemm; do python tools/ncu_summary.py gpurun_out/r2_prof_$f.ncu-rep > gpurun_out/r2_ncu_$f.txt 2>&1; done
