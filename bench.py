@@ -457,6 +457,11 @@ def workload_config(args, world, n_sites, trainable=None):  # noqa: ARG001 (trai
            "parallelism": "dp%d" % world, "layout": args.layout}
     kk = parse_geom(args.dw)[0] ** 2
     cfg["trainable_params"] = sum(ci * kk + co * ci for ci, co in plan_51m())
+    # (both arms print the same dict; these two describe how the CUDA arm launches and why it needs no L2 flush)
+    cfg["launch"] = ("CUDA graph of the pass replayed per step; per-kernel times = CUDA events inside the graph, last timed step" if args.graph else
+                     "stream launches; the timed region brackets the dominant family with CUDA events (roofline); the other families' "
+                     "times come from an instrumented pass of the same number of steps run just before it")
+    cfg["cache"] = "inputs larger than L2 (per-step working set of several GB >> 126 MB), no explicit flush"
     return cfg
 
 
@@ -870,7 +875,9 @@ def run_kdcc(args, rank, world, local_rank):
                     ms_ = sum(site_ms[site]) / len(site_ms[site])
                     row["kdcc_pw_fwd_ms"] = round(ms_, 4)
                     row["kdcc_pw_fwd_tflops"] = round(2.0 * row["mkn"][0] * row["mkn"][1] * row["mkn"][2] / (ms_ * 1e-3) / 1e12, 1)
-            gpu_baseline = {"what": "the reference's own torch calls for this path on this GPU (ATen / cuDNN / cuBLAS, TF32 off), ms per step "
+            gpu_baseline = {"note": "cuDNN's bf16 1x1 convolution needs a channels_last input; the kdcc GEMM runs on the reference's own NCHW "
+                                    "(and on planes -> channels_last inside a channels_last trunk).  pw_fwd is a tie with cuDNN, box to box 0.99 - 1.17x",
+                            "what": "the reference's own torch calls for this path on this GPU (ATen / cuDNN / cuBLAS, TF32 off), ms per step "
                                     "summed over the %d sites: fp32 NCHW as written and bf16 channels_last; pw_bwd = dX + dW; dw_bwd includes dX for every site" % len(plan),
                             "families": table, "matmul_bf16": gb["matmul_bf16"]}
         except Exception as exc:  # an annotation: never break the line
@@ -936,11 +943,7 @@ def run_kdcc(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": dict(workload_config(args, world, len(plan), hp.num_trainable),
-                           launch=("CUDA graph of the pass replayed per step; per-kernel times = CUDA events inside the graph, last timed step"
-                                   if use_graph else "stream launches; the timed region brackets the dominant family with CUDA events (roofline); the other "
-                                   "families' times come from an instrumented pass of the same number of steps run just before it"),
-                           cache="inputs larger than L2 (per-step working set of several GB >> 126 MB), no explicit flush"),
+            "config": workload_config(args, world, len(plan), hp.num_trainable),
             "grad_exchange": exchange,
             "clocks": clocks, "e2e": e2e, "gpu_launches": (hp.launches_per_step + (0 if args.torch_optimizer else 1)) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline, "api_modules": api, "whole_step": whole, "scaling_diag": scaling_diag,

@@ -43,7 +43,13 @@ class GradBucket:
         if peer and self.params and dev.type == "cuda" and dist.is_available() and dist.is_initialized() and \
                 dist.get_world_size(group) > 1 and hasattr(optimizer, "attach_grad_sources"):
             from .peer_reduce import PeerGradBucket
-            self.peer = PeerGradBucket(off, dev, group)
+            try:
+                self.peer = PeerGradBucket(off, dev, group)
+            except Exception as exc:   # no symmetric memory on this system: every rank falls back to the all-reduce alike
+                import warnings
+                warnings.warn("kdcc.GradBucket: peer gradient exchange unavailable (%r); using the NCCL all-reduce" % (exc,))
+                self.peer = None
+        if self.peer is not None:
             self.flat = self.peer.local()
             for p, o in zip(self.params, self.offsets):
                 optimizer.attach_grad_sources(p, lambda o=o, n=p.numel(): (self.peer.sources()[0][o:o + n],) + self.peer.sources()[1:])
@@ -52,6 +58,8 @@ class GradBucket:
                         lambda prm, o=o, n=p.numel(): self._push(o, o + n)))
         else:
             self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+            for p in self.params:   # a bucket rebuilt without the peer exchange must not leave stale sources behind
+                getattr(optimizer, "_sources", {}).pop(p, None)
         self._point_grads()
 
     def _point_grads(self):

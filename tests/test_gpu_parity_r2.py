@@ -273,3 +273,42 @@ def test_pointwise_planes_in_channels_last_out(kdcc, geom):
     assert relerr(host(y), ry) < TOL[dtype]
     assert relerr(host(xt.grad), rdx) < TOL[dtype]
     assert relerr(host(wt.grad), rdw) < TOL[dtype]
+
+
+def test_hot_path_step_orders_and_layouts_agree(kdcc):
+    """kdcc.hotpath.HotPathStep (what bench.py times): the reference loop's order (all forwards, losses, backward in reverse)
+    and the site-by-site order produce bit-identical losses and gradients (every kernel is deterministic), and the
+    channels_last form (inputs re-laid to planes, mixed-layout GEMMs) agrees with the NCHW form to bf16 accuracy.  Each
+    site is also checked against the oracle through its hint loss and pointwise weight gradient."""
+    from kdcc.hotpath import HotPathStep
+    from oracle import oracle as orc
+    plan = [(32, 64), (64, 32), (16, 48)]
+    N, H, W = 2, 40, 48
+    kw = dict(kernel_size=9, dilation=5, padding=20, dtype=torch.bfloat16, device="cuda", logits_shape=(N, 19, 32, 32),
+              need_dx=[False, True, True], seed=3)
+    steps = {name: HotPathStep(plan, N, H, W, order=order, layout=layout, **kw)
+             for name, order, layout in (("ref", "reference", "nchw"), ("inter", "interleaved", "nchw"), ("cl", "reference", "nhwc"))}
+    xs, ts, ls, lt = steps["ref"].make_inputs(seed=5)
+    out = {}
+    for name, hp in steps.items():
+        a, b = (xs, ts) if name != "cl" else ([x.permute(0, 2, 3, 1).contiguous() for x in xs], [t.permute(0, 2, 3, 1).contiguous() for t in ts])
+        hint, kd = hp.step(a, b, ls, lt)
+        torch.cuda.synchronize()
+        out[name] = (float(hint), float(kd), hp.flat_grads.clone(), hp.hint_losses.clone())
+    assert out["ref"][0] == out["inter"][0] and out["ref"][1] == out["inter"][1]
+    assert torch.equal(out["ref"][2], out["inter"][2])
+    assert abs(out["cl"][0] - out["ref"][0]) <= 2e-2 * abs(out["ref"][0])
+    assert relerr(host(out["cl"][2]), host(out["ref"][2])) < TOL[torch.bfloat16]
+    assert steps["cl"].relayout and steps["cl"].layout == kdcc._abi.NCHW
+    # site 0 against the oracle: hint loss value and the pointwise weight gradient
+    hp = steps["ref"]
+    a0, b0, c0 = hp._views[0]
+    ci, co = plan[0]
+    w_dw = host(hp.flat_params[a0:b0]).reshape(ci, 1, 9, 9)
+    w_pw = q(host(hp.flat_params[b0:c0]).reshape(co, ci, 1, 1), torch.bfloat16)
+    mid = q(orc.dw_fwd(host(xs[0]), w_dw, 9, 5, 20), torch.bfloat16)
+    y = q(orc.pw_fwd(mid, w_pw), torch.bfloat16)
+    loss, ds = orc.hint_loss(y, host(ts[0]), None, scale=1000.0)
+    assert abs(float(out["ref"][3][0]) - loss) <= 2e-2 * abs(loss)
+    _, rdw, _ = orc.pw_bwd(mid, w_pw, q(ds, torch.bfloat16), need_dx=False)
+    assert relerr(host(hp.flat_grads[b0:c0]).reshape(co, ci, 1, 1), rdw) < TOL[torch.bfloat16]

@@ -27,19 +27,38 @@ fam_of = {"cast_f32_to_bf16_kernel": "cast_w", "hint_loss_kernel": "hint_loss", 
           "kd_loss_kernel": "kd_loss", "reduce_splits_kernel": "pw_bwd_dw", "dw_tc_wgrad2_kernel": "dw_bwd(dW)",
           "dw_tc_wgrad2_reduce_kernel": "dw_bwd(dW)"}
 order = list(launch.values())
-# per site (kdcc.hotpath.HotPathStep.step): conv (fwd), GEMM fwd, hint, GEMM dW (+ split reduce), GEMM dX, [conv (dX) -- absent
-# when the site needs no input gradient], weight-gradient kernel (+ reduce).  A conv that directly follows a GEMM is the dX conv.
-gemm_seen = 0
+# kdcc.hotpath.HotPathStep.step in the reference loop's order: forward of every site (conv, GEMM), the hint losses, then the
+# backward in reverse site order (GEMM dW + split reduce, GEMM dX, [conv dX], weight-gradient kernel + reduce).  In the
+# site-by-site order a conv that directly follows a GEMM is the dX conv.  Both are told apart by what has been seen so far.
+hints_seen = bwd_gemms = 0
+interleaved = False
+names = [e["name"] for e in order]
+first_hint = names.index("hint_loss_kernel") if "hint_loss_kernel" in names else len(names)
+interleaved = names[:first_hint].count("dw_tc_conv2_kernel") == 1   # site-by-site: one forward conv before the first hint
 prev = ""
-for e in order:
+gemm_seen = 0
+for idx, e in enumerate(order):
     n = e["name"]
-    if n == "dw_tc_conv2_kernel":
-        e["fam"] = "dw_bwd(dX)" if prev == "pw_gemm_sm100_kernel" else "dw_fwd"
-    elif n == "pw_gemm_sm100_kernel":
-        e["fam"] = ("pw_fwd", "pw_bwd_dw", "pw_bwd_dx")[gemm_seen % 3]
-        gemm_seen += 1
+    if interleaved:
+        if n == "dw_tc_conv2_kernel":
+            e["fam"] = "dw_bwd(dX)" if prev == "pw_gemm_sm100_kernel" else "dw_fwd"
+        elif n == "pw_gemm_sm100_kernel":
+            e["fam"] = ("pw_fwd", "pw_bwd_dw", "pw_bwd_dx")[gemm_seen % 3]
+            gemm_seen += 1
+        else:
+            e["fam"] = fam_of.get(n, n)
     else:
-        e["fam"] = fam_of.get(n, n)
+        fwd_phase = idx < first_hint
+        if n == "dw_tc_conv2_kernel":
+            e["fam"] = "dw_fwd" if fwd_phase else "dw_bwd(dX)"
+        elif n == "pw_gemm_sm100_kernel":
+            if fwd_phase:
+                e["fam"] = "pw_fwd"
+            else:
+                e["fam"] = ("pw_bwd_dw", "pw_bwd_dx")[bwd_gemms % 2]
+                bwd_gemms += 1
+        else:
+            e["fam"] = fam_of.get(n, n)
     prev = n
 
 def to_bytes(e, key):
