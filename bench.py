@@ -929,8 +929,8 @@ def run_kdcc(args, rank, world, local_rank):
             dg, ag = lg.durations_ms(), hg.algorithmic()
             kernels_gscnn = {"img_per_s": round(2 * 5 / (g0.elapsed_time(g1) * 1e-3), 1), "ms_per_step": round(g0.elapsed_time(g1) / 5, 3),
                              "note": "cfg/cityscapes/51M_gscnn_all.json shapes: 9 sites on 128x256 maps (1024x2048 input), batch 2, k9 d5 p20, "
-                                     "WeightedHintMSELoss with a weight vector, KLDiv on (2,19,1024,2048); planes wider than 128 columns run "
-                                     "the tiled Toeplitz kernels (dw_tc.cu / dw_tc_wgrad.cu)"}
+                                     "WeightedHintMSELoss with a weight vector, KLDiv on (2,19,1024,2048); the 256-column planes run the whole-plane "
+                                     "convolution as two column halves (dw_tc2.cu), the weight gradient on the tiled kernel (dw_tc_wgrad.cu)"}
             for n_ in ("dw_fwd", "dw_bwd", "pw_fwd", "pw_bwd_dx", "pw_bwd_dw", "hint_loss", "kd_loss"):
                 ms_ = sum(dg[n_]) / 5
                 unit_ = ag[n_][1]

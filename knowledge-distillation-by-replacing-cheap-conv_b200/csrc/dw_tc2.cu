@@ -18,6 +18,13 @@
 //  * D = d accumulators of 128 x 32 fp32 in TMEM, double buffered; four epilogue warps re-interleave the phases in
 //    registers (thread = output row) and store bf16 rows.
 // The input-gradient form is the same kernel over dy with mirrored taps.
+//
+// Planes of 129 .. 256 columns (Gated-SCNN sites on a 1024 x 2048 input: 128 x 256) run as TWO column halves, each a
+// "virtual channel" with its own landing window and Toeplitz offset (9x9, dilation 5 only): the left half produces
+// columns [0, 120) from input columns [0, 160), the right half columns [120, W) from input columns [100, 260) (landed from
+// column 96: TMA wants a 16-byte aligned origin, the regrouping starts 4 columns in) -- both
+// windows are 32 phase-columns wide, so a half costs exactly what a 128-column plane costs (90 MMAs) instead of the
+// 180 of the tiled kernel (dw_tc.cu).  Split points are multiples of 5 (phases line up) and of 8 (16-byte store rows).
 // Reference semantics: models/students/transform_blocks/depthwise_separable_conv.py:7-8,12 (+ autograd).
 #include <stdlib.h>
 
@@ -42,6 +49,14 @@ struct C2Params {
   int chunks_p;   // K chunk slots per phase of the operand
   int planes, splits;
   long pairs;
+  int halves;     // 1; 2 = planes wider than 128 columns as two column halves (virtual channel = channel * halves + half)
+  int VC;         // C * halves
+  int in_x0[2], in_shift[2], out_x0[2], half_qoff[2], out_groups[2];  // per half: landing window start (a multiple of 8 columns:
+                  // TMA wants a 16-byte aligned origin) and whether the half's phase grid starts 4 columns into it, first output column, pad / dil seen
+                  // by its Toeplitz tiles, store tiles (groups of 8 * D columns)
+  int nbox;       // 64-column landing boxes per (half) plane
+  int nstg;       // landing stages: 2; 1 for the wide planes (their three boxes per stage would not fit twice)
+  int in_chunks;  // 16-byte chunks of a landed row the regrouping visits
   const float *w, *bias;
   __nv_bfloat16 *out;
   int dbg;  // KDCC_TC_DEBUG (timing experiments only): 1 skip Toeplitz rebuild, 2 skip MMAs, 4 skip stores, 8 skip regrouping
@@ -57,7 +72,8 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const uint32_t lbo = (uint32_t)p.rows_p * 16u;       // bytes between K chunks of the operand
   const uint32_t xp_bytes = (uint32_t)(D * p.chunks_p) * lbo;  // one operand buffer
-  const uint32_t xp_off = 2 * C2_STG;
+  const uint32_t stg_bytes = (uint32_t)p.nbox * (C2_STG / 2);     // one landing stage: nbox boxes of 128 rows x 128 bytes
+  const uint32_t xp_off = (uint32_t)p.nstg * stg_bytes;
   const uint32_t tz_off = xp_off + 2 * xp_bytes;
   const uint32_t tz_u = (uint32_t)(2 * p.ks) * C2_TZ_CHUNK;  // one tap row's Toeplitz tile: [2*ks K chunks][32][16 B]
   const uint32_t tz_bytes = (uint32_t)p.k * tz_u;
@@ -104,14 +120,15 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      // ===== TMA producer: one bare plane per item =====
+      // ===== TMA producer: one bare (half) plane per item =====
       int it = 0;
-      for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
-        const int s = it & 1;
-        ptx::mbar_wait(stg_empty(s), ((it >> 1) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(stg_full(s), C2_STG);
-        for (int b = 0; b < 2; ++b)
-          ptx::tma_load_4d(smem_base + s * C2_STG + b * (C2_STG / 2), &tm_in, stg_full(s), 64 * b, 0, w.channel(), w.pl);
+      for (PlaneWalk w(p.pairs, p.planes, p.splits, p.VC); w.valid(); w.next(), ++it) {
+        const int sl = it % p.nstg;
+        const int vc = w.channel(), c = vc / p.halves, h = vc % p.halves;
+        ptx::mbar_wait(stg_empty(sl), ((it / p.nstg) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(stg_full(sl), stg_bytes);
+        for (int b = 0; b < p.nbox; ++b)   // columns past the plane are zero-filled by the hardware
+          ptx::tma_load_4d(smem_base + sl * stg_bytes + b * (C2_STG / 2), &tm_in, stg_full(sl), p.in_x0[h] + 64 * b, 0, c, w.pl);
       }
     }
   } else if (warp == 1) {
@@ -127,7 +144,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       for (int b = 0; b < D; ++b) a_phase[b] = (uint32_t)(b * p.chunks_p) * chunk16;
       const uint32_t a_tile = 4u * chunk16, a_slice = 2u * chunk16;
       int it = 0, unit = -1;
-      for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+      for (PlaneWalk w(p.pairs, p.planes, p.splits, p.VC); w.valid(); w.next(), ++it) {
         const int s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         if (w.first_of_unit()) {
@@ -169,9 +186,10 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
   } else if (warp <= 5) {
     // ===== regrouping (128 threads, thread = plane row) + Toeplitz tiles =====
     const int r = threadIdx.x - 64;
-    const int nchunks = p.W >> 3;  // 16-byte chunks per plane row
-    auto build_t = [&](int c, int s) {
-      const float *wc = p.w + (long)c * p.k * p.k;
+    const int nchunks = p.in_chunks;  // 16-byte chunks of a landed row
+    auto build_t = [&](int vc, int s) {
+      const float *wc = p.w + (long)(vc / p.halves) * p.k * p.k;
+      const int qoff = p.half_qoff[vc % p.halves];
       uint8_t *ts = smem_gen + tz_off + (size_t)s * tz_bytes;
       // (tap row u, output phase-column q): tap v sits at reduction index q' = q - p/d + v
       for (int idx = r; idx < (KDCC_DBG(p, 1) ? 0 : p.k * 32); idx += 128) {
@@ -182,7 +200,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         for (int v = 0; v < 9; ++v) wv[v] = v < p.k ? __ldg(wr + (p.flip ? p.k - 1 - v : v)) : 0.f;
 #pragma unroll
         for (int v = 0; v < 9; ++v) {
-          const int qp = q - p.qoff + v + 8 * p.zpad;  // reduction index inside the N-tile's K window
+          const int qp = q - qoff + v + 8 * p.zpad;  // reduction index inside the N-tile's K window
           if (v < p.k && qp >= 0 && qp < 16 * p.ks)
             *reinterpret_cast<__nv_bfloat16 *>(ts + u * tz_u + (qp >> 3) * C2_TZ_CHUNK + q * 16 + (qp & 7) * 2) = __float2bfloat16_rn(wv[v]);
         }
@@ -192,10 +210,11 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       if (lane == 0) ptx::mbar_arrive(b_full(s));
     };
     int it = 0, unit = -1, built = 0;
-    PlaneWalk ahead(p.pairs, p.planes, p.splits, p.C);  // first plane of the next unit whose tiles are not built yet
-    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+    PlaneWalk ahead(p.pairs, p.planes, p.splits, p.VC);  // first plane of the next unit whose tiles are not built yet
+    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.VC); w.valid(); w.next(), ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
+      const int sl = it % p.nstg;
       // the MMAs of plane it-2 are done: operand buffer s is free
       ptx::mbar_wait(xp_empty(s), ph ^ 1);
       if (w.first_of_unit()) {
@@ -212,8 +231,9 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         ++built;
         ahead.next_unit();
       }
-      ptx::mbar_wait(stg_full(s), ph);
-      const uint8_t *stg = smem_gen + s * C2_STG;
+      ptx::mbar_wait(stg_full(sl), (it / p.nstg) & 1);
+      const uint8_t *stg = smem_gen + sl * stg_bytes;
+      const int shift = p.in_shift[w.channel() % p.halves];
       uint8_t *xp = smem_gen + xp_off + (size_t)s * xp_bytes + (size_t)(r + p.pad) * 16;
       if (!KDCC_DBG(p, 8)) {
 #pragma unroll 1
@@ -224,8 +244,16 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
           for (int j = 0; j < D; ++j) {
             const int c = g * D + j;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (c < nchunks)
-              v = *reinterpret_cast<const uint4 *>(stg + (c >> 3) * (C2_STG / 2) + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+            if (c < nchunks) {
+              if (!shift) {
+                v = *reinterpret_cast<const uint4 *>(stg + (c >> 3) * (C2_STG / 2) + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+              } else {  // the 8 columns start 4 columns (8 bytes) into landed chunk c: upper half of c, lower half of c + 1
+                const int c1 = c + 1;
+                const uint2 lo = *reinterpret_cast<const uint2 *>(stg + (c >> 3) * (C2_STG / 2) + r * 128 + (((c & 7) ^ (r & 7)) << 4) + 8);
+                const uint2 hi = *reinterpret_cast<const uint2 *>(stg + (c1 >> 3) * (C2_STG / 2) + r * 128 + (((c1 & 7) ^ (r & 7)) << 4));
+                v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+              }
+            }
             in[4 * j] = v.x; in[4 * j + 1] = v.y; in[4 * j + 2] = v.z; in[4 * j + 3] = v.w;
           }
 #pragma unroll
@@ -245,26 +273,26 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_arrive(xp_full(s));
-        ptx::mbar_arrive(stg_empty(s));
+        ptx::mbar_arrive(stg_empty(sl));
       }
     }
   } else {
     // ===== epilogue (128 threads, thread = output row = TMEM lane): re-interleave the phases in registers, stage
     // 32 rows x 8*D columns per warp in shared memory and let TMA store them (coalesced, clips ragged edges) =====
     const int quad = warp & 3;
-    const int nchunks = p.W >> 3;
     const uint32_t ob = ob_off + (uint32_t)(warp - 6) * 2 * OB;
     int it = 0, gi = 0;
-    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.C); w.valid(); w.next(), ++it) {
+    for (PlaneWalk w(p.pairs, p.planes, p.splits, p.VC); w.valid(); w.next(), ++it) {
       const int s = it & 1;
       ptx::mbar_wait(t_full(s), (it >> 1) & 1);
       ptx::tcgen05_fence_after();
-      const int c = w.channel();
+      const int c = w.channel() / p.halves, h = w.channel() % p.halves;
+      const int ngroups = p.out_groups[h], x0 = p.out_x0[h];
       const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
       const uint32_t t_row = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
       // a store tile = G groups of 8*D output columns (G chosen so that a tile row is 64-128 bytes)
 #pragma unroll 1
-      for (int g0 = 0; g0 * D < nchunks; g0 += G, ++gi) {
+      for (int g0 = 0; g0 < ngroups; g0 += G, ++gi) {
         if (gi >= 2) {  // the store that read this staging tile two tiles ago has finished reading it
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
@@ -273,7 +301,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 #pragma unroll
         for (int gg = 0; gg < G; ++gg) {
           const int g = g0 + gg;
-          if (g * D >= nchunks) break;
+          if (g >= ngroups) break;
           uint32_t v[D][8];
 #pragma unroll
           for (int b = 0; b < D; ++b) ptx::tmem_ld_32x32b_x8(t_row + (uint32_t)((b * p.nt + (g >> 2)) * 32 + (g & 3) * 8), v[b]);
@@ -292,7 +320,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !KDCC_DBG(p, 4)) {
-          ptx::tma_store_4d(&tm_out, smem_base + tile, 8 * D * g0, 32 * quad, c, w.pl);
+          ptx::tma_store_4d(&tm_out, smem_base + tile, x0 + 8 * D * g0, 32 * quad, c, w.pl);
           ptx::tma_store_commit();
         }
       }
@@ -311,8 +339,15 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// planes of 129 .. 256 columns as two column halves: derived for the 9 x 9, dilation 5, pad 20 geometry (split at column 120)
+static bool conv2_wide(int Hi, int Wi, int Ho, int Wo, int k, int dil, int pad) {
+  return Hi == Ho && Wi == Wo && Hi <= 128 && Wi > 128 && Wi <= 256 && Wi % 8 == 0 && k == 9 && dil == 5 && pad == 20 &&
+         !getenv("KDCC_DW_CONV2_NO_WIDE");
+}
+
 bool dw_tc_conv2_supported(int Hi, int Wi, int Ho, int Wo, int k, int dil, int pad) {
   if (getenv("KDCC_DW_CONV_V1")) return false;
+  if (conv2_wide(Hi, Wi, Ho, Wo, k, dil, pad)) return true;
   const int halo = dil * (k - 1);
   if (Hi != Ho || Wi != Wo || Hi > 128 || Wi > 128 || Wi % 8 != 0) return false;
   if (k % 2 == 0 || k > 9 || halo > 48 || 2 * pad != halo || pad % dil != 0) return false;
@@ -340,7 +375,7 @@ static int conv2_launch(const void *in, C2Params p, cudaStream_t st) {
   const uint32_t obox[4] = {8 * D * (D == 1 ? 4 : (D == 2 ? 2 : 1)), 32, 1, 1};
   rc = make_tmap_bf16(&tm_out, p.out, 4, dims, strides, obox, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  const int smem = 2 * C2_STG + 2 * D * p.chunks_p * p.rows_p * 16 + 2 * p.k * 2 * p.ks * C2_TZ_CHUNK + 128 + 8 * 32 * 16 * D * (D == 1 ? 4 : (D == 2 ? 2 : 1)) + 256 + 1024;
+  const int smem = p.nstg * p.nbox * (C2_STG / 2) + 2 * D * p.chunks_p * p.rows_p * 16 + 2 * p.k * 2 * p.ks * C2_TZ_CHUNK + 128 + 8 * 32 * 16 * D * (D == 1 ? 4 : (D == 2 ? 2 : 1)) + 256 + 1024;
   if (smem > 227 * 1024 || D * p.nt * 32 > 256) return KDCC_ESHAPE;
   static int attr_cache[16] = {0};
   if (int e = ensure_dynamic_smem(dw_tc_conv2_kernel<D, NT, KS>, smem, attr_cache)) return e;
@@ -355,7 +390,8 @@ int dw_tc_conv2(const void *in, const float *w, const float *bias, void *out, in
   p.N = N; p.C = C; p.H = H; p.W = W; p.k = k; p.dil = dil; p.pad = pad; p.flip = flip;
   p.rows_p = 128 + dil * (k - 1);
   p.qoff = pad / dil;
-  const int Q = (W + dil - 1) / dil;  // columns of one phase
+  const bool wide = W > 128;
+  const int Q = ((wide ? 160 : W) + dil - 1) / dil;  // columns of one phase (of one half's window)
   p.nt = (Q + 31) / 32;
   if (p.nt == 1) {  // the whole phase is one N-tile: its K window is the phase itself (pad columns do not exist)
     p.zpad = 0;
@@ -366,9 +402,24 @@ int dw_tc_conv2(const void *in, const float *w, const float *bias, void *out, in
     p.ks = ((31 + k - 1 - p.qoff + 8 * p.zpad) / 8 + 1 + 1) / 2;
     p.chunks_p = 4 * (p.nt - 1) + 2 * p.ks;
   }
+  p.halves = wide ? 2 : 1;
+  p.VC = C * p.halves;
+  if (!wide) {
+    p.in_x0[0] = 0; p.in_shift[0] = 0; p.out_x0[0] = 0; p.half_qoff[0] = p.qoff;
+    p.out_groups[0] = ((W >> 3) + dil - 1) / dil;
+    p.nbox = 2; p.nstg = 2; p.in_chunks = W >> 3;
+  } else {
+    // left half: outputs q in [0, 24) of every phase = columns [0, 120), inputs q' in [0, 32) = columns [0, 160);
+    // right half: outputs q in [24, 52) = columns [120, W), inputs q' in [20, 52) = columns [100, 260): the window starts
+    // qoff = 4 phase-columns before its first output, so its Toeplitz tiles see pad / dil = 0.  TMA needs a 16-byte aligned
+    // column origin: the right window is landed from column 96 and regrouped from 4 columns in.
+    p.in_x0[0] = 0;  p.in_shift[0] = 0; p.out_x0[0] = 0;   p.half_qoff[0] = p.qoff; p.out_groups[0] = 3;
+    p.in_x0[1] = 96; p.in_shift[1] = 1; p.out_x0[1] = 120; p.half_qoff[1] = 0;      p.out_groups[1] = ((W - 120) + 39) / 40;
+    p.nbox = 3; p.nstg = 1; p.in_chunks = 20;
+  }
   p.planes = N;
-  p.splits = tc_unit_splits(C, N);
-  p.pairs = (long)C * p.splits;
+  p.splits = tc_unit_splits(p.VC, N);
+  p.pairs = (long)p.VC * p.splits;
   p.w = w; p.bias = bias;
   p.out = static_cast<__nv_bfloat16 *>(out);
   if (N == 0 || C == 0) return KDCC_OK;

@@ -312,3 +312,30 @@ def test_hot_path_step_orders_and_layouts_agree(kdcc):
     assert abs(float(out["ref"][3][0]) - loss) <= 2e-2 * abs(loss)
     _, rdw, _ = orc.pw_bwd(mid, w_pw, q(ds, torch.bfloat16), need_dx=False)
     assert relerr(host(hp.flat_grads[b0:c0]).reshape(co, ci, 1, 1), rdw) < TOL[torch.bfloat16]
+
+
+@pytest.mark.parametrize("geom", [(2, 8, 8, 128, 256), (3, 24, 16, 100, 200), (1, 8, 16, 64, 136), (1, 40, 8, 128, 248)])
+def test_wide_planes_run_as_two_column_halves(kdcc, geom):
+    """Planes of 129 .. 256 columns (Gated-SCNN sites on a 1024 x 2048 input, BASELINE config 4) on the whole-plane
+    tensor-core convolution: two column halves with their own landing window and Toeplitz offset; forward, dX and dW against
+    the oracle (fp32 taps un-rounded), and bit-identical to the tiled kernel's result semantics at the seam columns."""
+    from test_gpu_parity import oracle_block
+    N, Ci, Co, H, W = geom
+    k, d, p = 9, 5, 20
+    dtype = torch.bfloat16
+    rs = np.random.RandomState(7 + W + Ci)
+    x = rs.standard_normal((N, Ci, H, W)).astype(np.float32)
+    w_dw = (rs.uniform(-1, 1, (Ci, 1, k, k)) / k).astype(np.float32)
+    w_pw = (rs.uniform(-1, 1, (Co, Ci, 1, 1)) / np.sqrt(Ci)).astype(np.float32)
+    dy = rs.standard_normal((N, Co, H, W)).astype(np.float32)
+    y, dx, dwd, dwp = run_block(kdcc, x, w_dw, w_pw, dy, k, d, p, dtype, layout="nchw")
+    ry, rdx, rdwd, rdwp = oracle_block(x, w_dw, w_pw, dy, k, d, p, dtype)
+    for name, mine, ref in (("y", y, ry), ("dx", dx, rdx), ("dw_dw", dwd, rdwd), ("dw_pw", dwp, rdwp)):
+        assert relerr(mine, ref) < TOL[dtype], name
+    # the depthwise alone, column by column around the seam (columns 100 .. 160 are touched by both halves' windows)
+    from oracle import oracle as orc
+    xt = torch.from_numpy(x).cuda().to(dtype)
+    mid = kdcc.functional.depthwise_conv(xt, torch.from_numpy(w_dw).cuda(), None, k, d, p)
+    ref_mid = orc.dw_fwd(host(xt), w_dw, k, d, p)
+    err_cols = np.abs(host(mid) - ref_mid).max(axis=(0, 1, 2)) / np.abs(ref_mid).max()
+    assert err_cols.max() < TOL[dtype], int(err_cols.argmax())
