@@ -815,6 +815,26 @@ def run_kdcc(args, rank, world, local_rank):
             if per_step_ms > dom_ms:
                 dominant, dom_ms = name, per_step_ms
         kernels[name] = entry
+    # per-site times of every family (instrumented pass, plan order): which site shapes run at which rate
+    per_site = {}
+    try:
+        order_of = list(range(len(plan)))
+        for name in ("dw_fwd", "pw_fwd", "hint_loss", "pw_bwd_dw", "pw_bwd_dx", "dw_bwd"):
+            lst = full_durs.get(name, [])
+            if len(lst) != args.steps * len(plan):
+                continue
+            backward = name in ("pw_bwd_dw", "pw_bwd_dx", "dw_bwd") and args.order == "reference"   # reverse site order
+            ms = [0.0] * len(plan)
+            for idx, v in enumerate(lst):
+                pos = idx % len(plan)
+                ms[len(plan) - 1 - pos if backward else pos] += v / args.steps
+            per_site[name] = [round(v, 4) for v in ms]
+        per_site["sites"] = ["%d->%d" % s_ for s_ in plan]
+        for name, key in (("pw_fwd", "pw_fwd_tflops"), ("pw_bwd_dw", "pw_bwd_dw_tflops"), ("pw_bwd_dx", "pw_bwd_dx_tflops")):
+            if name in per_site:
+                per_site[key] = [round(2.0 * N * maps * maps * ci * co / (t_ * 1e-3) / 1e12, 1) for (ci, co), t_ in zip(plan, per_site[name])]
+    except Exception:
+        per_site = None
     dk = kernels[dominant]
     # measured DRAM traffic of the dominant family over one step: ncu dram__bytes_read.sum + dram__bytes_write.sum of
     # every launch of one step of this same default workload (tools/gpu_profile.sh -> profiles/r01_traffic.json)
@@ -947,7 +967,7 @@ def run_kdcc(args, rank, world, local_rank):
             "grad_exchange": exchange,
             "clocks": clocks, "e2e": e2e, "gpu_launches": (hp.launches_per_step + (0 if args.torch_optimizer else 1)) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline, "api_modules": api, "whole_step": whole, "scaling_diag": scaling_diag,
-            "kernels": kernels, "kernels_k3": kernels_k3, "kernels_gscnn": kernels_gscnn, "losses": {"hint": float(hint), "kd": float(kd)}}
+            "kernels": kernels, "kernels_per_site": per_site, "kernels_k3": kernels_k3, "kernels_gscnn": kernels_gscnn, "losses": {"hint": float(hint), "kd": float(kd)}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -37,7 +37,13 @@ constexpr int GEMM_BR = 64;    // reduction elements per stage = one 128-byte sw
 // drain, so the default stays 4 (tools/build_variant.sh builds the other one).
 constexpr int GEMM_EPI_WARPS = KDCC_GEMM_EPI_WARPS;
 constexpr int GEMM_EPI_HALVES = GEMM_EPI_WARPS / 4;
-constexpr int GEMM_EPI_TILES = GEMM_EPI_WARPS == 4 ? 2 : 1;   // staging tiles per epilogue warp (32 KB in all)
+#ifndef KDCC_GEMM_EPI_TILES
+#define KDCC_GEMM_EPI_TILES (KDCC_GEMM_EPI_WARPS == 4 ? 2 : 1)
+#endif
+#ifndef KDCC_GEMM_PAIR_STAGES
+#define KDCC_GEMM_PAIR_STAGES 6
+#endif
+constexpr int GEMM_EPI_TILES = KDCC_GEMM_EPI_TILES;   // staging tiles (4 KB) per epilogue warp: TMA stores in flight per warp
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 struct GemmParams {
@@ -69,7 +75,7 @@ struct GemmCfg {
   static constexpr int BJ_CTA = PAIR ? BJ / 2 : BJ;       // B rows held by one CTA
   static constexpr int B_BYTES = BJ_CTA * GEMM_BR * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = PAIR ? 6 : (BJ == 256 ? 4 : (BJ == 128 ? 6 : 8));
+  static constexpr int STAGES = PAIR ? KDCC_GEMM_PAIR_STAGES : (BJ == 256 ? 4 : (BJ == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BJ;  // double-buffered accumulator (power of two >= 32)
   static constexpr int OUT_OFF = STAGES * STAGE_BYTES;   // epilogue staging: tiles of 32 rows x 128 bytes per warp
   static constexpr int BAR_OFF = OUT_OFF + GEMM_EPI_WARPS * GEMM_EPI_TILES * 4096;
@@ -248,7 +254,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           ptx::tmem_ld_32x32b_x32(t_row + ch * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           ptx::tmem_ld_wait();
           if (tn >= GEMM_EPI_TILES) {  // the store that last read this staging tile has finished reading it
-            if (lane == 0) { if (GEMM_EPI_TILES == 2) ptx::tma_store_wait_read1(); else ptx::tma_store_wait_read(); }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(GEMM_EPI_TILES - 1) : "memory");
             __syncwarp();
           }
           const uint32_t tile = stage_tiles + (uint32_t)(tn % GEMM_EPI_TILES) * 4096;
