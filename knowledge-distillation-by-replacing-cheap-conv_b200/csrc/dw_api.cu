@@ -56,8 +56,8 @@ KDCC_API size_t kdcc_dw_bwd_workspace_bytes(int N, int H, int W, int C, int k, i
   int Ho, Wo;
   if (check_geometry(N, H, W, C, k, dil, pad, layout, dtype, &Ho, &Wo) || N == 0) return 0;
   if (layout == KDCC_LAYOUT_NCHW) {
-    const size_t a = dw_tc_wgrad_workspace(N, C, Ho, Wo, k), b = dw_tc_wgrad2_workspace(N, C, k);
-    return a > b ? a : b;
+    const size_t a = dw_tc_wgrad_workspace(N, C, Ho, Wo, k), b = dw_tc_wgrad2_workspace(N, C, k), c = dw_tc_wgrad3_workspace(N, C);
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);
   }
   const int vn = dtype == KDCC_F32 ? 4 : 8;
   size_t splits = (size_t)dw_direct_wgrad_splits(N, Ho, C, k, vn);
@@ -94,6 +94,8 @@ KDCC_API int kdcc_dw_bwd(const void *x, const float *w, const void *dy, void *dx
       if (rc) return rc;
     }
     if (dw) {
+      if (dw_tc_wgrad3_supported(H, W, Ho, Wo, k, dil, pad))
+        return dw_tc_wgrad3(x, dy, dw, static_cast<float *>(workspace), N, C, H, W, st);
       if (dw_tc_wgrad2_supported(H, W, Ho, Wo, k, dil, pad))
         return dw_tc_wgrad2(x, dy, dw, static_cast<float *>(workspace), N, C, H, W, k, dil, pad, st);
       return dw_tc_wgrad(x, dy, dw, static_cast<float *>(workspace), N, C, H, W, Ho, Wo, k, dil, pad, st);

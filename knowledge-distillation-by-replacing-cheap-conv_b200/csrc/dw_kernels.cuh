@@ -49,5 +49,10 @@ bool dw_tc_wgrad2_supported(int H, int W, int Ho, int Wo, int k, int dil, int pa
 int dw_tc_wgrad2(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, int k, int dil,
                  int pad, cudaStream_t st);
 size_t dw_tc_wgrad2_workspace(int N, int C, int k);
+int dw_tc_wgrad2_reduce(const float *part, float *dw, int splits, long count, cudaStream_t st);  // dw = sum over splits, fixed order
+// column-phase variant for the 9 x 9, dilation 5, pad 20 geometry (H, W <= 128): dw_tc_wgrad3.cu
+bool dw_tc_wgrad3_supported(int H, int W, int Ho, int Wo, int k, int dil, int pad);
+int dw_tc_wgrad3(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, cudaStream_t st);
+size_t dw_tc_wgrad3_workspace(int N, int C);
 
 }  // namespace kdcc

@@ -275,6 +275,11 @@ __global__ void dw_tc_wgrad2_reduce_kernel(const float *__restrict__ part, float
   dw[i] = acc;
 }
 
+int dw_tc_wgrad2_reduce(const float *part, float *dw, int splits, long count, cudaStream_t st) {
+  launch_pdl(dw_tc_wgrad2_reduce_kernel, dim3((unsigned)ceil_div<long>(count, 256)), dim3(256), 0, st, part, dw, splits, count);
+  return launch_status();
+}
+
 template <int K>
 static int wgrad2_launch(const void *x, const void *dy, float *dw, float *part, W2Params p, cudaStream_t st) {
   CUtensorMap tm_x, tm_dy;
@@ -293,9 +298,7 @@ static int wgrad2_launch(const void *x, const void *dy, float *dw, float *part, 
   launch_pdl(dw_tc_wgrad2_kernel<K>, dim3(grid), dim3(W2_THREADS), (size_t)smem, st, tm_x, tm_dy, p);
   rc = launch_status();
   if (rc || p.splits == 1) return rc;
-  const long count = (long)p.C * K * K;
-  launch_pdl(dw_tc_wgrad2_reduce_kernel, dim3((unsigned)ceil_div<long>(count, 256)), dim3(256), 0, st, part, dw, p.splits, count);
-  return launch_status();
+  return dw_tc_wgrad2_reduce(part, dw, p.splits, (long)p.C * K * K, st);
 }
 
 int dw_tc_wgrad2(const void *x, const void *dy, float *dw, float *part, int N, int C, int H, int W, int k, int dil,
