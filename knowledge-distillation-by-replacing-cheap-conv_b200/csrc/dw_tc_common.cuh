@@ -8,20 +8,27 @@ namespace kdcc {
 // among `splits` CTAs.  A CTA keeps per-channel state (the Toeplitz operand, the k*k gradient partials) across
 // the planes of a unit.  Every warp role walks the same sequence.
 struct PlaneWalk {
-  long pair, pairs, stride;
-  int pl, planes, splits, C;
+  // 32-bit arithmetic: units = channels x splits is far below 2^31, and a 64-bit division by a run-time value is a
+  // ~100-instruction subroutine that the single issuing thread of a kernel would pay once or twice per plane
+  unsigned pair, pairs, stride, C;
+  int pl, planes, splits, sp, ch;  // sp / ch: split and channel of the current unit
   __device__ PlaneWalk(long pairs_, int planes_, int splits_, int C_)
-      : pair(blockIdx.x), pairs(pairs_), stride(gridDim.x), planes(planes_), splits(splits_), C(C_) {
-    pl = (int)(pair / C);
+      : pair(blockIdx.x), pairs((unsigned)pairs_), stride(gridDim.x), C((unsigned)C_), planes(planes_), splits(splits_) {
+    locate();
     settle();
   }
+  __device__ void locate() {
+    sp = (int)(pair / C);
+    ch = (int)(pair - (unsigned)sp * C);
+    pl = sp;
+  }
   __device__ void settle() {  // skip units whose split owns no plane
-    while (pair < pairs && pl >= planes) { pair += stride; pl = (int)(pair / C); }
+    while (pair < pairs && pl >= planes) { pair += stride; locate(); }
   }
   __device__ bool valid() const { return pair < pairs; }
-  __device__ int channel() const { return (int)(pair % C); }
-  __device__ int split() const { return (int)(pair / C); }
-  __device__ bool first_of_unit() const { return pl == split(); }
+  __device__ int channel() const { return ch; }
+  __device__ int split() const { return sp; }
+  __device__ bool first_of_unit() const { return pl == sp; }
   __device__ bool last_of_unit() const { return pl + splits >= planes; }
   __device__ void next() {
     pl += splits;
@@ -29,7 +36,7 @@ struct PlaneWalk {
   }
   __device__ void next_unit() {
     pair += stride;
-    pl = (int)(pair / C);
+    locate();
     settle();
   }
 };

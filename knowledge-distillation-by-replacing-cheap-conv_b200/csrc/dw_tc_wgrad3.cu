@@ -29,6 +29,17 @@
 // Shared memory: 2 x 32 KB landing, 2 x 52.5 KB x operand, 40 KB dy operand.  TMEM: 2 x 64 columns transposed dy (halves of
 // a phase), 2 x 3 x 32 accumulators, 2 x 72 columns A slots, 16 columns S.
 // Deterministic: fixed-order sums, no atomics; splits are reduced by dw_tc_wgrad2's reduce kernel.
+//
+// Measured (4096 channels x 4 images, same box): 0.298 ms against 0.46 ms for dw_tc_wgrad2 -- 5.0 kclk per plane where the
+// tensor work is 2.8 and shared memory 3.3.  What is left is hand-off latency: a phase is only ~550 clocks of tensor work, and
+// on this chip an mbarrier hand-off between two warps costs ~180 clocks, one through tcgen05.commit ~240, a tcgen05.ld + wait
+// ~160 when idle and ~340 under these MMAs (tools/hop_probe.cu, the hand-off trace of a debug build): the chain transposing MMA
+// -> commit -> converters load -> release -> store -> product MMA runs once per phase.  Variants that were built and measured
+// on the same box: a second issuing thread for the transposing MMAs (equal), a ring of three half-phase tiles
+// with the third tap-row group single-buffered to pay for it in TMEM (slower: 0.317), per-phase hand-over of single operand
+// buffers behind double landing buffers (slower: ten fence.proxy.async + hops per plane on the regrouping warps), two sets of
+// converter warps alternating phases at 72 registers (equal).  The TMEM budget (512 columns: 128 tile + 192 accumulators +
+// 144 A slots + 16 S) is what keeps the transposition from running two phases ahead.
 // Reference semantics: autograd of models/students/transform_blocks/depthwise_separable_conv.py:12.
 #include <stdlib.h>
 
@@ -201,7 +212,7 @@ dw_tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       constexpr uint32_t main_hi = (W3_XLBO >> 4) | (1u << 14);
       const uint32_t main_lo0 = (((smem_base + W3_OFF_XO) & 0x3FFFF) >> 4) | ((128u >> 4) << 16);
       const uint32_t t_sel = tmem_base + W3_T_SEL;
-      long n = 0;  // phase counter: 5 * plane + phase
+      uint32_t n = 0;  // phase counter: 5 * plane + phase
       // transposing MMAs of phase b of plane t (phase counter m): S (128 x 32) . dy_b^T -> rows [0, 64) and [64, 128)
       auto issue_sel = [&](int t, int b, long m) {
         ptx::mbar_wait(do_full(b), (uint32_t)(t & 1));
@@ -318,6 +329,7 @@ dw_tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       const int ab = unit & 1;
       ptx::mbar_wait(acc_full(ab), (uint32_t)(unit >> 1) & 1);
       ptx::tcgen05_fence_after();
+      __syncwarp();
       float *out = p.out + ((long)w.split() * p.C + w.channel()) * (W3_K * W3_K);
 #pragma unroll 1
       for (int g = 0; g < 3; ++g) {
@@ -354,7 +366,7 @@ dw_tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const uint32_t quad = ((uint32_t)(jj * 32)) << 16;
     const int sh = W3_D * jj;
     const bool odd = (jj & 1) != 0, edge = odd && h == 1;
-    long n = 0;
+    uint32_t n = 0;
     for (PlaneWalk w(p.units, p.N, p.splits, p.C); w.valid(); w.next()) {
 #pragma unroll 1
       for (int b = 0; b < W3_D; ++b, ++n) {
@@ -362,6 +374,7 @@ dw_tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         ptx::mbar_wait(dt_full(h), (uint32_t)(n & 1));
         if (edge) ptx::mbar_wait(dt_full(0), (uint32_t)(n & 1));
         ptx::tcgen05_fence_after();
+        __syncwarp();
         uint32_t r0[32], r1[32];
         uint32_t carry = 0u;
         const uint32_t src = tmem_base + W3_T_DT + quad + 64u * h;
@@ -377,6 +390,7 @@ dw_tc_wgrad3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         }
         ptx::mbar_wait(a_empty(as), (uint32_t)((n >> 1) & 1) ^ 1);  // the product MMAs of phase n-2 are done
         ptx::tcgen05_fence_after();
+        __syncwarp();
         const uint32_t dst = tmem_base + W3_T_A + (uint32_t)as * W3_A_COLS + quad;
         if (!KDCC_DBG(p, 4)) {
           uint32_t o[16];

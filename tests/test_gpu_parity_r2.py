@@ -339,3 +339,35 @@ def test_wide_planes_run_as_two_column_halves(kdcc, geom):
     ref_mid = orc.dw_fwd(host(xt), w_dw, k, d, p)
     err_cols = np.abs(host(mid) - ref_mid).max(axis=(0, 1, 2)) / np.abs(ref_mid).max()
     assert err_cols.max() < TOL[dtype], int(err_cols.argmax())
+
+
+@pytest.mark.parametrize("geom", [(1, 8, 128, 128), (3, 37, 128, 128), (2, 16, 96, 104), (5, 300, 128, 128), (2, 40, 65, 128),
+                                  (1, 3, 128, 8), (4, 512, 128, 128)])
+def test_depthwise_weight_gradient_column_phase_kernel(kdcc, geom):
+    """9 x 9, dilation 5 weight gradient on the column-phase tensor-core kernel (dw_tc_wgrad3.cu: four tap rows per MMA, dy
+    transposed by the tensor core) over ragged planes, odd batch sizes and channel counts that split units across CTAs:
+    against torch's fp64 autograd of the reference's depthwise conv (depthwise_separable_conv.py:12) and against the
+    whole-plane kernel it replaces (KDCC_DW_WGRAD_V2=1).  Both operands are exact bf16 and the sums are fp32: 2e-5."""
+    n, c, h, w_ = geom
+    gen = torch.Generator("cuda").manual_seed(11)
+    x = torch.randn(n, c, h, w_, device="cuda", generator=gen).to(torch.bfloat16)
+    dy = torch.randn(n, c, h, w_, device="cuda", generator=gen).to(torch.bfloat16)
+    w = torch.randn(c, 1, 9, 9, device="cuda", generator=gen) * 0.1
+
+    def grad():
+        wt = w.detach().clone().requires_grad_(True)
+        kdcc.functional.depthwise_conv(x, wt, None, 9, 5, 20).backward(dy)
+        return wt.grad.detach().clone()
+
+    mine = grad()
+    wd = w.double().requires_grad_(True)
+    torch.nn.functional.conv2d(x.double(), wd, None, 1, 20, 5, c).backward(dy.double())
+    ref = wd.grad
+    assert ((mine.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5
+    os.environ["KDCC_DW_WGRAD_V2"] = "1"
+    try:
+        old = grad()
+    finally:
+        del os.environ["KDCC_DW_WGRAD_V2"]
+    assert ((mine - old).abs().max() / old.abs().max()).item() < 2e-5
+    assert torch.equal(mine, grad())  # deterministic: fixed-order sums, no atomics

@@ -55,6 +55,10 @@ __device__ __forceinline__ void mma_ws_ts(uint32_t d, uint32_t a_tmem, uint32_t 
   MMA_TS(".ws.cta_group::1.kind::f16");
 }
 
+// g_nacc: accumulators the MMA loop rotates over (0 = as many as fit, up to 4; 1 = every MMA accumulates into the same tile)
+// g_bmode: 0 = B K-major; 1 = B MN-major without swizzle, 8-column chunks 168 rows apart, start row 20 * (j % 3) (dw_tc_wgrad3.cu)
+__constant__ int g_nacc, g_bmode;
+
 template <int mode>
 __global__ void __launch_bounds__(512, 1) probe(int M, int N, int iters, long long *out) {
   extern __shared__ uint8_t smem_raw[];
@@ -74,18 +78,20 @@ __global__ void __launch_bounds__(512, 1) probe(int M, int N, int iters, long lo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if constexpr (mode <= WSTS) {
     if (threadIdx.x < 32 && ptx::elect_one()) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24) | (g_bmode ? (1u << 16) : 0u);
       const uint32_t a_base = base, b_base = base + 96 * 1024;
       const uint32_t hi = (128u >> 4) | (1u << 14);  // 8-row groups 128 B apart, version 1, no swizzle
+      const uint32_t bhi = g_bmode ? ((168u * 16u) >> 4) | (1u << 14) : hi;
       const uint32_t a_lo = ((a_base & 0x3FFFF) >> 4) | ((uint32_t)((168 * 16) >> 4) << 16);  // K chunks 168 rows apart
-      const uint32_t b_lo = ((b_base & 0x3FFFF) >> 4) | ((uint32_t)((N * 16) >> 4) << 16);
-      const int nacc = 448 / N < 4 ? (448 / N < 2 ? 1 : 2) : 4;
+      const uint32_t b_lo = ((b_base & 0x3FFFF) >> 4) | ((uint32_t)(((g_bmode ? 128 : N * 16)) >> 4) << 16);
+      const int nacc = g_nacc ? g_nacc : (448 / N < 4 ? (448 / N < 2 ? 1 : 2) : 4);
+      const uint32_t bstep = g_bmode ? 20u : 0u;
       const long long t0 = clock64();
       for (int i = 0; i < iters; i += 12) {
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
           const uint32_t d = tmem + (uint32_t)(j % nacc) * (uint32_t)N;
-          const uint32_t a_j = a_lo + (uint32_t)j * 5u, b_j = b_lo + (uint32_t)(j & 1) * 2u;
+          const uint32_t a_j = a_lo + (uint32_t)j * 5u, b_j = b_lo + (uint32_t)(j & 1) * 2u + (uint32_t)(j % 3) * bstep;
           const uint32_t a_t = tmem + 480u + (uint32_t)(j & 1) * 8u;
           if constexpr (mode == SS) mma_ss(d, a_j, hi, b_j, hi, idesc);
           else if constexpr (mode == SSUSE) {
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(512, 1) probe(int M, int N, int iters, long lo
             if (j % 3 == 0) mma_ss_fill(d, a_g, hi, b_j, hi, idesc);
             else if (j % 3 == 1) mma_ss_use(d, a_g, hi, b_j, hi, idesc);
             else mma_ss_last(d, a_g, hi, b_j, hi, idesc);
-          } else if constexpr (mode == TS) mma_ts(d, a_t, b_j, hi, idesc);
+          } else if constexpr (mode == TS) mma_ts(d, a_t, b_j, bhi, idesc);
           else if constexpr (mode == WSSS) mma_ws_ss(d, a_j, hi, b_j, hi, idesc);
           else mma_ws_ts(d, a_t, b_j, hi, idesc);
         }
@@ -185,6 +191,9 @@ int main(int argc, char **argv) {
   for (int i = 0; i < 8; ++i) if (!strcmp(argv[1], names[i])) mode = i;
   if (mode < 0) return 2;
   const int M = argc > 2 ? atoi(argv[2]) : 128, N = argc > 3 ? atoi(argv[3]) : 32, warps = argc > 4 ? atoi(argv[4]) : 4;
+  const int nacc = mode <= WSTS && argc > 4 ? atoi(argv[4]) : 0, bmode = argc > 5 ? atoi(argv[5]) : 0;
+  cudaMemcpyToSymbol(g_nacc, &nacc, sizeof(int));
+  cudaMemcpyToSymbol(g_bmode, &bmode, sizeof(int));
   long long *d_out;
   cudaMalloc(&d_out, 4096 * sizeof(long long));
   const int iters = mode <= WSTS ? 4092 : 4096;
@@ -199,7 +208,7 @@ int main(int argc, char **argv) {
   long long mx = 0, mi = 0;
   for (int b = 0; b < 148; ++b) { if (h[2 * b + 1] > mx) mx = h[2 * b + 1]; if (h[2 * b] > mi) mi = h[2 * b]; }
   if (mode <= WSTS)
-    printf("%-5s M %3d N %3d: issue %.1f clk/mma, complete %.1f clk/mma\n", argv[1], M, N, (double)mi / iters, (double)mx / iters);
+    printf("%-5s M %3d N %3d nacc %d bmode %d: issue %.1f clk/mma, complete %.1f clk/mma\n", argv[1], M, N, nacc, bmode, (double)mi / iters, (double)mx / iters);
   else if (mode == SHFL)
     printf("%-5s warps %2d: %.2f clk per warp-shfl per SM (%.2f per warp)\n", argv[1], warps, (double)mx / iters / warps, (double)mx / iters);
   else
