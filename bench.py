@@ -152,9 +152,10 @@ class ClockSampler:
 # tensor-core depthwise kernels (measured rates: tools/tc_probe2.cu -> profiles/r02_tc_probe2.txt):
 #   conv (dw_tc2.cu): 90 SS MMAs x (4 KB image slab + 1 KB Toeplitz chunk) = 450 KB of operand reads, TMA landing 32 KB,
 #     regrouping 32 KB read + 40 KB written, epilogue staging 32 KB written + 32 KB read by the TMA store        = 618 KB
-#   dW (dw_tc_wgrad2.cu): 72 TS MMAs x 4 KB of B = 288 KB, TMA landing 64 KB, dy transposition (2-byte reads use half a
-#     wavefront: 64 KB), diagonal extraction through the scratch rows (write 180 KB + read 52 KB)                  = 648 KB
-SMEM_BYTES_PER_PLANE = {"conv": 618 * 1024, "wgrad": 648 * 1024}
+#   dW (dw_tc_wgrad3.cu): 130 product MMAs x 1 KB of B + 20 transposing MMAs x 2 KB of B = 170 KB, TMA landing 64 KB,
+#     regrouping of x and dy 2 x (32 KB read + 40 KB written)                                                     = 378 KB
+#     (dw_tc_wgrad2.cu, which it replaced for this geometry, moved 648 KB and 4.6 kclk of mostly discarded tensor math)
+SMEM_BYTES_PER_PLANE = {"conv": 618 * 1024, "wgrad": 378 * 1024}
 SMEM_BYTES_PER_CLK = 128
 
 
@@ -172,7 +173,7 @@ def smem_floor(plan, batch, geom, layout, maps, need_dx, measured_ms, sm_mhz, sm
     clk = (planes_dx * SMEM_BYTES_PER_PLANE["conv"] + planes_dw * SMEM_BYTES_PER_PLANE["wgrad"]) / float(SMEM_BYTES_PER_CLK) / sms
     floor_ms = clk / (sm_mhz * 1e3)
     return {"ms": round(floor_ms, 3), "frac": round(floor_ms / measured_ms, 4), "sm_mhz": sm_mhz,
-            "model": "(%d dX planes x 618 KB + %d dW planes x 648 KB) / 128 B/clk / %d SMs" % (planes_dx, planes_dw, sms)}
+            "model": "(%d dX planes x 618 KB + %d dW planes x 378 KB) / 128 B/clk / %d SMs" % (planes_dx, planes_dw, sms)}
 
 
 def cpu_reference_image_seconds(plan, maps, geom, budget_s, crop):

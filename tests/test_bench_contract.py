@@ -42,8 +42,8 @@ def test_smem_floor_model():
     plan = bench.plan_51m()
     need_dx = [False] + [True] * (len(plan) - 1)
     planes = 4 * sum(ci for ci, _ in plan)
-    f = bench.smem_floor(plan, 4, (9, 5, 20), "nchw", 128, need_dx, 3.15, 1900.0)
-    want = ((planes - 4 * plan[0][0]) * 618 * 1024 + planes * 648 * 1024) / 128 / 148 / 1.9e6
+    f = bench.smem_floor(plan, 4, (9, 5, 20), "nchw", 128, need_dx, 2.66, 1900.0)
+    want = ((planes - 4 * plan[0][0]) * 618 * 1024 + planes * 378 * 1024) / 128 / 148 / 1.9e6
     assert abs(f["ms"] - want) < 1e-3 and 0 < f["frac"] < 1
     assert bench.smem_floor(plan, 4, (9, 5, 20), "nhwc", 128, need_dx, 3.15, 1900.0) is None
     assert bench.smem_floor(plan, 4, (9, 5, 20), "nchw", 128, need_dx, 3.15, None) is None

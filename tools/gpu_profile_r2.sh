@@ -20,10 +20,10 @@ timeout -s KILL 600 ncu --metrics $M --clock-control none --profile-from-start o
 echo "step metrics rc=$?"
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:dw_tc_conv2 -s 11 -c 2 -o gpurun_out/r2_prof_conv2 -f python bench.py $B > gpurun_out/r2_ncu_full1.out 2>&1
 echo "full conv2 rc=$?"
-timeout -s KILL 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:dw_tc_wgrad2_kernel -s 6 -c 1 -o gpurun_out/r2_prof_wgrad2 -f python bench.py $B > gpurun_out/r2_ncu_full2.out 2>&1
-echo "full wgrad2 rc=$?"
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:dw_tc_wgrad3_kernel -s 6 -c 1 -o gpurun_out/r2_prof_wgrad3 -f python bench.py $B > gpurun_out/r2_ncu_full2.out 2>&1
+echo "full wgrad3 rc=$?"
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:pw_gemm -s 18 -c 3 -o gpurun_out/r2_prof_gemm -f python bench.py $B > gpurun_out/r2_ncu_full3.out 2>&1
 echo "full gemm rc=$?"
 python tools/step_metrics_summary.py gpurun_out/r2_step_metrics.csv gpurun_out/r2_step_metrics.txt gpurun_out/r2_traffic.json | tail -20
-for f in conv2 wgrad2 gemm; do python tools/ncu_summary.py gpurun_out/r2_prof_$f.ncu-rep > gpurun_out/r2_ncu_$f.txt 2>&1; done
+for f in conv2 wgrad3 gemm; do python tools/ncu_summary.py gpurun_out/r2_prof_$f.ncu-rep > gpurun_out/r2_ncu_$f.txt 2>&1; done
 ls -la gpurun_out | grep -E "r2_.*(ncu-rep|csv|txt|json)"

@@ -24,7 +24,7 @@ for r in rows:
 
 # bench family of every launch, from the fixed per-site order of kdcc.hotpath.HotPathStep.step
 fam_of = {"cast_f32_to_bf16_kernel": "cast_w", "hint_loss_kernel": "hint_loss", "loss_finalize_kernel": "loss_finalize",
-          "kd_loss_kernel": "kd_loss", "reduce_splits_kernel": "pw_bwd_dw", "dw_tc_wgrad2_kernel": "dw_bwd(dW)",
+          "kd_loss_kernel": "kd_loss", "reduce_splits_kernel": "pw_bwd_dw", "dw_tc_wgrad2_kernel": "dw_bwd(dW)", "dw_tc_wgrad3_kernel": "dw_bwd(dW)",
           "dw_tc_wgrad2_reduce_kernel": "dw_bwd(dW)"}
 order = list(launch.values())
 # kdcc.hotpath.HotPathStep.step in the reference loop's order: forward of every site (conv, GEMM), the hint losses, then the
