@@ -19,6 +19,6 @@ print('gpu_baseline', d['gpu_baseline'] and {k: (v['kdcc_ms'], v['speedup_vs_bes
 print('k3', d['kernels_k3'])
 print('gscnn', d['kernels_gscnn'] and {k: d['kernels_gscnn'][k] for k in ('img_per_s', 'ms_per_step', 'dw_fwd', 'dw_bwd') if k in d['kernels_gscnn']})
 r = json.loads(open('gpurun_out/bench_reference.json').read().strip().splitlines()[-1])
-print('reference', r.get('value'), r.get('unit'), r.get('cpu_baseline', {}).get('cores'), r.get('whole_step'), 'same config:', r.get('config') == {k: v for k, v in d['config'].items() if k not in ('launch', 'cache')})
+print('reference', r.get('value'), r.get('unit'), r.get('cpu_baseline', {}).get('cores'), r.get('whole_step'), 'same config:', r.get('config') == d['config'])
 PY
 if [ -n "$PROFILE" ]; then bash tools/gpu_profile_r2.sh; fi
