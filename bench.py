@@ -851,7 +851,7 @@ def run_kdcc(args, rank, world, local_rank):
     if dominant.startswith("dw") and k >= 7:
         note = ("achieved = algorithmic bytes of all %d launches of one step / their CUDA-event time; traffic = ncu DRAM bytes of the "
                 "same launches.  k=9 depthwise is 81 MAC per output element (20 MAC per HBM byte): the kernels run on tcgen05 and are "
-                "bound by the 128 B/clk shared-memory data path that feeds the MMAs (618 KB per plane for the conv, 648 KB for dW: "
+                "bound by the 128 B/clk shared-memory data path that feeds the MMAs (618 KB per plane for the conv, 378 KB for dW: "
                 "smem_floor; DESIGN.md 4.0/4.1), not by HBM; frac is still reported against the HBM copy peak.  Against the stock "
                 "torch CUDA kernels for the same call the family is ~50x faster (gpu_baseline)" % dk["launches_per_step"])
     roofline = {"kernel": dominant, "bound": dk["bound"], "achieved": dk["achieved"],
