@@ -253,6 +253,7 @@ dw_tc_conv_kernel(const __grid_constant__ CUtensorMap tm_in, const DwTcParams p)
       decode(cur.pl, n, i0, j0);
       ptx::mbar_wait(t_full(s), ph);
       ptx::tcgen05_fence_after();
+      __syncwarp();  // lanes leave the polling loop one by one; the TMEM accesses below are .sync.aligned
       const int gi = i0 + quad * 32 + lane;
       const float bias = p.bias ? __ldg(p.bias + c) : 0.f;
       __nv_bfloat16 *orow = p.out + (((long)n * p.C + c) * p.Ho + gi) * p.Wo + j0;

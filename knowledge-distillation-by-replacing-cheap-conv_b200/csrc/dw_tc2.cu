@@ -286,6 +286,7 @@ dw_tc_conv2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_const
       const int s = it & 1;
       ptx::mbar_wait(t_full(s), (it >> 1) & 1);
       ptx::tcgen05_fence_after();
+      __syncwarp();  // lanes leave the polling loop one by one; the TMEM accesses below are .sync.aligned
       const int c = w.channel() / p.halves, h = w.channel() % p.halves;
       const int ngroups = p.out_groups[h], x0 = p.out_x0[h];
       const float bias = p.bias ? __ldg(p.bias + c) : 0.f;

@@ -262,6 +262,7 @@ dw_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         if (tb != grp) continue;  // the other group drains this accumulator
         ptx::mbar_wait(t_full(tb), (tit >> 1) & 1);
         ptx::tcgen05_fence_after();
+        __syncwarp();  // lanes leave the polling loop one by one; the TMEM accesses below are .sync.aligned
         const uint32_t t_row = tmem_base + (tb ? WG_TMEM_D1 : 0u) + ((uint32_t)(quad * 32) << 16);
         for (int c3 = 0; c3 < (KDCC_DBG(p, 1) ? 0 : nch); ++c3) {
           const int col0 = 32 * (quad + c3);

@@ -161,9 +161,11 @@ dw_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       const int np = min(2, p.N - 2 * w.pl);
       ptx::mbar_wait(a_empty(s), ph ^ 1);  // the MMAs that read this TMEM stage two pairs ago are done
       ptx::tcgen05_fence_after();
+      __syncwarp();  // lanes leave the polling loop one by one; the TMEM accesses below are .sync.aligned
       for (int pl = 0; pl < 2; ++pl) {
         if (pl < np) {
           ptx::mbar_wait(dy_full, (uint32_t)(pit & 1));
+          __syncwarp();
           const uint32_t t_dst = tmem_base + (uint32_t)((s * 2 + pl) * 64) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -210,6 +212,7 @@ dw_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         const int tb = tit & 1;
         ptx::mbar_wait(t_full(tb), (tit >> 1) & 1);
         ptx::tcgen05_fence_after();
+        __syncwarp();  // lanes leave the polling loop one by one; the TMEM accesses below are .sync.aligned
         const uint32_t t_row = tmem_base + W2_TMEM_P + (uint32_t)tb * 128u + ((uint32_t)(quad * 32) << 16);
         for (int col0 = c_first; col0 <= c_last && !KDCC_DBG(p, 1); col0 += 32) {
           if (col0 < 0 || col0 >= 128) continue;

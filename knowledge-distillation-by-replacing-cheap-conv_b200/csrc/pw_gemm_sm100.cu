@@ -240,6 +240,7 @@ pw_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       const long obase = tile_batch * p.out_batch_stride;
       ptx::mbar_wait(tfull_bar(as), aph);
       ptx::tcgen05_fence_after();
+      __syncwarp();  // lanes leave the polling loop one by one; the TMEM accesses below are .sync.aligned
       const int row = ti * GEMM_BI + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (uint32_t)(as * BJ) + ((uint32_t)(quad * 32) << 16);
       if (p.tma_out) {
