@@ -38,8 +38,10 @@
 // on the same box: a second issuing thread for the transposing MMAs (equal), a ring of three half-phase tiles
 // with the third tap-row group single-buffered to pay for it in TMEM (slower: 0.317), per-phase hand-over of single operand
 // buffers behind double landing buffers (slower: ten fence.proxy.async + hops per plane on the regrouping warps), two sets of
-// converter warps alternating phases at 72 registers (equal).  The TMEM budget (512 columns: 128 tile + 192 accumulators +
-// 144 A slots + 16 S) is what keeps the transposition from running two phases ahead.
+// converter warps alternating phases at 72 registers (equal), two transposed tiles with the transposition two phases ahead
+// and one accumulator set (0.303 vs 0.293), sixteen converter warps of 32 rows each (0.351 vs 0.303).  tcgen05.ld does not slow
+// the MMAs down, but beside them a warp gets one x32 load per ~240 clk (tools/tc_probe2 "ts 128 32 3 1 8": 134 B/clk/SM for
+// eight warps, 239 idle): the converters' 320 KB per plane are latency-, not bandwidth-bound.
 // Reference semantics: autograd of models/students/transform_blocks/depthwise_separable_conv.py:12.
 #include <stdlib.h>
 

@@ -57,7 +57,7 @@ __device__ __forceinline__ void mma_ws_ts(uint32_t d, uint32_t a_tmem, uint32_t 
 
 // g_nacc: accumulators the MMA loop rotates over (0 = as many as fit, up to 4; 1 = every MMA accumulates into the same tile)
 // g_bmode: 0 = B K-major; 1 = B MN-major without swizzle, 8-column chunks 168 rows apart, start row 20 * (j % 3) (dw_tc_wgrad3.cu)
-__constant__ int g_nacc, g_bmode;
+__constant__ int g_nacc, g_bmode, g_ldwarps;  // g_ldwarps: warps 4.. read TMEM (tcgen05.ld x32 + wait, or st x32 if negative) while the MMAs run
 
 template <int mode>
 __global__ void __launch_bounds__(512, 1) probe(int M, int N, int iters, long long *out) {
@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(512, 1) probe(int M, int N, int iters, long lo
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
   __shared__ long long wclk[16];
+  __shared__ volatile int stop_flag;
+  __shared__ unsigned int ld_ops[32];
+  if (threadIdx.x == 0) stop_flag = 0;
   for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(gen)[i] = 0x3c003c00u + (i & 3);
   if (threadIdx.x == 0) { ptx::mbar_init(ptx::smem_u32(&bar), 1); ptx::fence_barrier_init(); }
   if (threadIdx.x < 32) ptx::tmem_alloc<512>(ptx::smem_u32(&slot));
@@ -110,6 +113,34 @@ __global__ void __launch_bounds__(512, 1) probe(int M, int N, int iters, long lo
       const long long t2 = clock64();
       out[2 * blockIdx.x] = t1 - t0;
       out[2 * blockIdx.x + 1] = t2 - t0;
+      stop_flag = 1;
+    }
+    if (warp >= 4) {  // background TMEM traffic from other warps (their quadrant, columns 256..383: not the MMA's tiles)
+      const uint32_t t_row = tmem + 256u + ((uint32_t)((warp & 3) * 32) << 16);
+      unsigned int ops = 0;
+      uint32_t acc = 0, r[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) r[q] = q;
+      while (!stop_flag) {
+        if (g_ldwarps > 0) {
+          ptx::tmem_ld_32x32b_x32(t_row + (ops & 3) * 32u, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) acc ^= r[q];
+        } else {
+          ptx::tmem_st_32x32b_x32(t_row + (ops & 3) * 32u, r);
+          ptx::tmem_st_wait();
+        }
+        ++ops;
+      }
+      if (lane == 0) ld_ops[warp] = ops;
+      if (acc == 0x12345678u) out[500] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
+      for (int w = 4; w < (int)(blockDim.x >> 5); ++w) tot += ld_ops[w];
+      out[400 + blockIdx.x] = (long long)tot;
     }
   } else {
     uint32_t acc = 0;
@@ -191,13 +222,14 @@ int main(int argc, char **argv) {
   for (int i = 0; i < 8; ++i) if (!strcmp(argv[1], names[i])) mode = i;
   if (mode < 0) return 2;
   const int M = argc > 2 ? atoi(argv[2]) : 128, N = argc > 3 ? atoi(argv[3]) : 32, warps = argc > 4 ? atoi(argv[4]) : 4;
-  const int nacc = mode <= WSTS && argc > 4 ? atoi(argv[4]) : 0, bmode = argc > 5 ? atoi(argv[5]) : 0;
+  const int nacc = mode <= WSTS && argc > 4 ? atoi(argv[4]) : 0, bmode = argc > 5 ? atoi(argv[5]) : 0, ldwarps = argc > 6 ? atoi(argv[6]) : 0;
+  cudaMemcpyToSymbol(g_ldwarps, &ldwarps, sizeof(int));
   cudaMemcpyToSymbol(g_nacc, &nacc, sizeof(int));
   cudaMemcpyToSymbol(g_bmode, &bmode, sizeof(int));
   long long *d_out;
   cudaMalloc(&d_out, 4096 * sizeof(long long));
   const int iters = mode <= WSTS ? 4092 : 4096;
-  const int threads = mode <= WSTS ? 128 : 32 * warps;
+  const int threads = mode <= WSTS ? 128 + 32 * abs(ldwarps) : 32 * warps;
   for (int rep = 0; rep < 2; ++rep) {
     launch(mode, threads, M, N, iters, d_out);
     cudaError_t e = cudaDeviceSynchronize();
@@ -207,6 +239,12 @@ int main(int argc, char **argv) {
   cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
   long long mx = 0, mi = 0;
   for (int b = 0; b < 148; ++b) { if (h[2 * b + 1] > mx) mx = h[2 * b + 1]; if (h[2 * b] > mi) mi = h[2 * b]; }
+  if (mode <= WSTS && ldwarps) {
+    long long ops[148];
+    cudaMemcpy(ops, d_out + 400, sizeof(ops), cudaMemcpyDeviceToHost);
+    printf("  with %d warps doing tcgen05.%s x32 + wait: %.1f B/clk/SM of TMEM traffic beside the MMAs\n", abs(ldwarps), ldwarps > 0 ? "ld" : "st",
+           4096.0 * ops[0] / (double)h[1]);
+  }
   if (mode <= WSTS)
     printf("%-5s M %3d N %3d nacc %d bmode %d: issue %.1f clk/mma, complete %.1f clk/mma\n", argv[1], M, N, nacc, bmode, (double)mi / iters, (double)mx / iters);
   else if (mode == SHFL)
